@@ -1,0 +1,193 @@
+/*
+ * stoch_gpmp_b200 — C-ABI of the B200-native StochGPMP hot path.
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * replaces one piece of arithmetic that the reference (anindex/stoch_gpmp, pure Python on PyTorch)
+ * performs inside `StochGPMP.reset()/optimize()`; the citation on each function is the reference
+ * file:line it stands in for.  The reference-side binding (ctypes) is shown in INTEGRATION.md and
+ * implemented in stoch_gpmp_b200/_lib.py.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers unless marked (host);
+ *   - `dtype` selects the arithmetic/storage type `real` of every `void*` array: SGPMP_F32 or SGPMP_F64;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous,
+ *     nothing here synchronises the device;
+ *   - every function returns an sgpmp status code (0 = OK) and never throws; sgpmp_last_error()
+ *     gives a thread-local text for the last non-OK status;
+ *   - shapes: B problems, G goals, K particle means per goal, NP = G*K particles, S samples per
+ *     particle, T support states, n DoF, d = 2n (state = [pos(n), vel(n)]), M = T*d.
+ *
+ * Memory layouts (row-major, last index fastest)
+ *   means    [B, NP, T, d]      == reference `particle_means` [NP,T,d] per problem (planner.py:215)
+ *   samples  [B, NP, T, d, S]   "S-minor": consecutive samples are consecutive in memory so that one
+ *                               thread per sample reads/writes fully coalesced.  The reference's logical
+ *                               `state_samples[p, s, t, j]` (planner.py:243, itself a non-contiguous
+ *                               transposed view) is samples[b, p, t, j, s]; the Python host returns
+ *                               permuted views, no copy.
+ *   eps      same layout as samples
+ *   costs / weights [B, NP, S]
+ *   tables   [T, SGPMP_TABLE_STRIDE] doubles per prior, see sgpmp_prior_factor
+ */
+#ifndef STOCH_GPMP_B200_H
+#define STOCH_GPMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPMP_ABI_VERSION 1
+
+enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
+
+enum {
+    SGPMP_OK = 0,
+    SGPMP_ERR_INVALID_ARG = 1,
+    SGPMP_ERR_UNSUPPORTED = 2, /* shape not instantiated (e.g. n_dof) — the host raises NotImplementedError */
+    SGPMP_ERR_CUDA = 3,
+    SGPMP_ERR_NO_DEVICE = 4
+};
+
+#define SGPMP_TABLE_STRIDE 16
+/* column indices of one table row (time step t, one DoF; all DoF share the tables) */
+enum {
+    SGPMP_TAB_G11 = 0, SGPMP_TAB_G21 = 1, SGPMP_TAB_G22 = 2,                      /* G_t = A_t^-T (lower)          */
+    SGPMP_TAB_H11 = 3, SGPMP_TAB_H12 = 4, SGPMP_TAB_H21 = 5, SGPMP_TAB_H22 = 6,   /* H_t = G_t C_{t-1}^T, H_0 = 0  */
+    SGPMP_TAB_D11 = 7, SGPMP_TAB_D12 = 8, SGPMP_TAB_D22 = 9,                      /* P[t,t]                        */
+    SGPMP_TAB_O11 = 10, SGPMP_TAB_O12 = 11, SGPMP_TAB_O21 = 12, SGPMP_TAB_O22 = 13 /* P[t+1,t] (zero row T-1)      */
+};
+
+#define SGPMP_MAX_FRAMES 16
+#define SGPMP_MAX_SPHERES 16
+#define SGPMP_NUM_TERMS 5
+enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_COLL = 3, SGPMP_TERM_IS = 4 };
+
+/* Problem-batch shape.  problem_gid0 is the GLOBAL index of problem 0 of this shard: the Philox
+ * counters are keyed by global problem/particle ids so that results do not depend on how the batch is
+ * sharded over GPUs. */
+typedef struct sgpmp_shape {
+    int32_t B, G, K, S, T, n_dof;
+    int32_t dtype;
+    int32_t reserved;
+    int64_t problem_gid0;
+} sgpmp_shape_t;
+
+/* Lowered form of the reference's cost objects (what StochGPMP.__init__ extracts from cost.cost_list):
+ *   CostGP          cost_functions.py:90-146   sigma_start, sigma_gp, start_state, dt
+ *   CostGoalPrior   cost_functions.py:342-388  sigma_goal_prior, multi_goal_states
+ *   CostCollision   cost_functions.py:223-261  sigma_coll + field:
+ *       ObstacleMap         envs/obst_map.py:108-188     (occupancy grid lookup)
+ *       LinkDistanceField   costs/fields.py:30-86 'rbf'  (FK link positions vs obstacle spheres)
+ *   IS term         planner.py:233-236         temperature * x^T Sigma^-1 mu
+ * FK chain = the callable the reference passes as CostComposite(FK=...) (cost_functions.py:39-52),
+ * restated as a serial chain of fixed transforms + revolute z joints. */
+typedef struct sgpmp_cost_desc {
+    double dt;
+    double sigma_start;
+    double sigma_gp;
+    double sigma_goal_prior;  /* <= 0: no CostGoalPrior term */
+    double temperature;       /* weight of the IS term; 0 disables it */
+
+    const void* start;        /* [B, d] real */
+    const void* goals;        /* [B, G, d] real, or NULL */
+
+    /* occupancy map field (NULL = absent) */
+    const void* occ_map;             /* [n_maps, map_h, map_w] real; value = map[iy][ix] */
+    const int32_t* map_of_problem;   /* [B] map index per problem, or NULL => map 0 */
+    int32_t n_maps, map_h, map_w;
+    int32_t origin_xi, origin_yi;
+    int32_t reserved0;
+    double map_inv_cell;             /* 1/cell_size exactly as the reference forms it (obst_map.py:172) */
+    double map_sigma_coll;
+
+    /* sphere field (NULL = absent); needs the FK chain */
+    const void* spheres;             /* [B, n_spheres, 4] or [n_spheres, 4] real: (cx, cy, cz, r) */
+    int32_t n_spheres;
+    int32_t spheres_per_problem;     /* 1: [B,O,4]; 0: one set shared by all problems */
+    double sphere_sigma_coll;
+
+    /* FK chain (host data, copied into kernel parameters) */
+    int32_t n_frames;                /* <= SGPMP_MAX_FRAMES; frames after the base */
+    int32_t include_base;            /* 1: the base frame (identity, origin) is also a link position */
+    double chain_R[SGPMP_MAX_FRAMES][9];  /* fixed rotation parent->child, row-major */
+    double chain_p[SGPMP_MAX_FRAMES][3];  /* fixed translation parent->child */
+    int32_t chain_joint[SGPMP_MAX_FRAMES];/* joint index rotating about child z, or -1 (fixed) */
+} sgpmp_cost_desc_t;
+
+int sgpmp_abi_version(void);
+const char* sgpmp_last_error(void);
+/* 1 if the cost / fused kernels are instantiated for this DoF count (sampling / prior are generic). */
+int sgpmp_dof_supported(int32_t n_dof);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
+int64_t sgpmp_launch_count(void);
+
+/* K1 — prior factor.  Replaces MultivariateNormal(precision_matrix=...) construction
+ * (mp_priors_multi.py:100-110 -> torch multivariate_normal.py:79-85) for the block-tridiagonal
+ * constant-velocity precision of mp_priors_multi.py:170-202, per DoF (2x2 blocks), in fp64.
+ *   D [n_priors, T, 3]   (d11, d12, d22) of P[t,t]
+ *   O [n_priors, T-1, 4] (o11, o12, o21, o22) of P[t+1,t]
+ *   tables [n_priors, T, 16] out;  not_pd [n_priors] out: 0, or 1 + index of the failing pivot block
+ * One thread per prior runs the reverse block Cholesky P = U U^T. */
+int sgpmp_prior_factor(int32_t n_priors, int32_t T, const double* D, const double* O,
+                       double* tables, int32_t* not_pd, void* stream);
+
+/* Dense scale_tril L [M, M] (row-major, `dtype`) expanded from one prior's tables — the matrix the
+ * reference holds as dist._unbroadcasted_scale_tril (multivariate_normal.py:196).  Test / interop aid. */
+int sgpmp_prior_dense_L(int32_t T, int32_t n_dof, const double* tables, int32_t dtype, void* L, void* stream);
+
+/* K2 — sampling x = mu + L eps (mp_priors_multi.py:204-207 -> multivariate_normal.py:251-254) as the
+ * banded recurrence y_t = G_t eps_t - H_t y_{t-1}.
+ *   eps_in  NULL: draw eps in-kernel (Philox4x32-10 keyed by seed/draw/global ids);
+ *           else: use these normals (parity with the reference's torch-drawn eps)
+ *   eps_out optional: the normals that were used
+ * Here the "particles" axis is generic: for the INIT prior pass G as NP (K=1 in shape) and S = K. */
+int sgpmp_sample(const sgpmp_shape_t* shape, const double* tables, const void* means,
+                 const void* eps_in, uint64_t seed, uint32_t draw,
+                 void* samples, void* eps_out, void* stream);
+
+/* K3 — per-trajectory-sample cost: CostComposite.eval (cost_functions.py:47-58) + the IS term
+ * (planner.py:229-237).  costs [B,NP,S]; terms optional [SGPMP_NUM_TERMS, B, NP, S].
+ * means == NULL drops the IS term (then tables may be NULL): that is CostComposite.eval alone. */
+int sgpmp_cost(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+               const void* samples, const void* means, void* costs, void* terms, void* stream);
+
+/* Link-frame origins by the same FK code the cost kernel uses: q [n_cfg, n_dof] -> pos [n_cfg, L, 3],
+ * L = n_frames + include_base; only the chain fields of `desc` are read.  Stands in for the FK callable
+ * of CostComposite (cost_functions.py:51-52) when checking collision-freeness of final plans. */
+int sgpmp_fk_link_positions(const sgpmp_cost_desc_t* desc, int32_t n_dof, int32_t dtype, int32_t n_cfg,
+                            const void* q, void* pos, void* stream);
+
+/* K4 — softmax over the S samples of each particle + weighted-mean update
+ * (StochGPMP._update_distribution, planner.py:263-275).  means is updated in place;
+ * grad [B,NP,T,d] and weights [B,NP,S] are optional outputs. */
+int sgpmp_update(const sgpmp_shape_t* shape, double temperature, double step_size,
+                 const void* costs, const void* samples, void* means, void* grad, void* weights,
+                 void* stream);
+
+/* Fused optimisation loop: n_iters iterations of sample -> cost -> softmax -> update
+ * (StochGPMP.optimize, planner.py:277-317) in ONE launch, one CTA per (problem, particle); samples are
+ * never written to HBM except, optionally, those of the last iteration.
+ *   eps_in     NULL (in-kernel Philox, draw index = draw0 + iteration) or [n_iters, B, NP, T, d, S]
+ *   means      in/out; means_pre out (optional): the means BEFORE the last iteration's update, which is
+ *              what optimize() returns (planner.py:252-253)
+ *   samples    optional out, last iteration only;  costs/weights/grad optional outs, last iteration */
+int sgpmp_iterate(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+                  double step_size, int32_t n_iters, const void* eps_in, uint64_t seed, uint32_t draw0,
+                  void* means, void* means_pre, void* samples, void* costs, void* weights, void* grad,
+                  void* stream);
+
+/* Split-particle mode (one problem's samples sharded over ranks).  Local statistics of
+ * this rank's S_local samples per particle:  stats[B,NP, 2 + M] = (m, Z, A[M]) with
+ *   m = max_s(-c_s/tau), Z = sum_s exp(-c_s/tau - m), A = sum_s exp(-c_s/tau - m) eps_s.
+ * After the cross-rank log-sum-exp merge (NCCL, done by the host), sgpmp_apply_stats applies
+ * mu += step * L (A/Z). */
+int sgpmp_local_stats(const sgpmp_shape_t* shape, double temperature, const void* costs, const void* eps,
+                      void* stats, void* stream);
+int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size,
+                      const void* stats, void* means, void* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOCH_GPMP_B200_H */

@@ -1,0 +1,84 @@
+"""Oracle: per-trajectory-sample cost terms.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Reference call sites restated (all in /root/reference/stoch_gpmp):
+  CostComposite.eval   costs/cost_functions.py:47-58   sum of children in list order, b = p*S + s
+  CostGP.eval          costs/cost_functions.py:128-146 start + GP transition quadratic forms
+  GPFactor.get_error   costs/factors/gp_factor.py:54-58   e_t = x_{t+1} - Phi x_t
+  UnaryFactor          costs/factors/unary_factor.py:19-23
+  CostGoalPrior.eval   costs/cost_functions.py:376-388 goal of particle p is p // K
+  CostCollision.eval   costs/cost_functions.py:247-261 + FieldFactor.get_error
+                       costs/factors/field_factor.py:18-32  (time steps 1..T-1 only)
+  ObstacleMap.get_collisions  envs/obst_map.py:164-182
+  LinkDistanceField.compute_cost ('rbf')  costs/fields.py:63-79
+  importance-sampling term    planner.py:229-237   tau * x^T Sigma^-1 mu
+
+Every function takes samples x [NP, S, T, d] and returns [NP, S].
+"""
+import numpy as np
+
+from . import prior as _prior
+
+
+def cost_start(x, start_state, sigma_start):
+    e = start_state[None, None, :] - x[:, :, 0, :]
+    return (e * e).sum(-1) / sigma_start ** 2
+
+
+def cost_gp(x, dt, sigma_gp):
+    d = x.shape[-1]
+    n = d // 2
+    p, v = x[..., :n], x[..., n:]
+    ep = p[:, :, 1:] - p[:, :, :-1] - dt * v[:, :, :-1]
+    ev = v[:, :, 1:] - v[:, :, :-1]
+    qc = 1.0 / sigma_gp ** 2
+    q11, q12, q22 = 12.0 * dt ** -3.0 * qc, -6.0 * dt ** -2.0 * qc, 4.0 * dt ** -1.0 * qc
+    return (q11 * ep * ep + 2.0 * q12 * ep * ev + q22 * ev * ev).sum((-1, -2))
+
+
+def cost_goal_prior(x, goal_states, K, sigma_goal_prior):
+    NP = x.shape[0]
+    g = np.arange(NP) // K
+    e = goal_states[g][:, None, :] - x[:, :, -1, :]
+    return (e * e).sum(-1) / sigma_goal_prior ** 2
+
+
+def map_lookup(xy, occ_map, cell_size, origin_xi, origin_yi):
+    """Occupancy lookup with the reference's exact arithmetic order, in xy's dtype:
+    X*(1/cell) + offset  (two roundings, no FMA) -> floor -> int -> clamp -> map[iy, ix].
+    Note the reference clamps ix with shape[0] and iy with shape[1] (obst_map.py:177-178)."""
+    dt = xy.dtype.type
+    inv = dt(1.0 / cell_size)
+    xo = (xy[..., 0] * inv + dt(origin_xi))
+    yo = (xy[..., 1] * inv + dt(origin_yi))
+    ix = np.clip(np.floor(xo).astype(np.int64), 0, occ_map.shape[0] - 1)
+    iy = np.clip(np.floor(yo).astype(np.int64), 0, occ_map.shape[1] - 1)
+    return occ_map[iy, ix]
+
+
+def cost_collision_map(x, occ_map, cell_size, origin_xi, origin_yi, sigma_coll):
+    vals = map_lookup(x[:, :, 1:, :2], occ_map, cell_size, origin_xi, origin_yi)
+    return vals.sum(-1).astype(x.dtype) * (1.0 / sigma_coll ** 2)
+
+
+def sphere_rbf(link_pos, spheres):
+    """link_pos [..., L, 3], spheres [O, 4] -> [...]: sum_l sum_o exp(-0.5 |p-c|^2 / r^2)."""
+    diff = link_pos[..., :, None, :] - spheres[None, :, :3]
+    return np.exp(-0.5 * (diff * diff).sum(-1) / (spheres[:, 3] ** 2)).sum((-1, -2))
+
+
+def cost_collision_spheres(x, spheres, sigma_coll, fk_fn):
+    """fk_fn: q [N, n] -> H [N, L, 4, 4]."""
+    NP, S, T, d = x.shape
+    n = d // 2
+    q = x[:, :, 1:, :n].reshape(-1, n)
+    H = fk_fn(q)
+    pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
+    return sphere_rbf(pos, spheres).sum(-1) * (1.0 / sigma_coll ** 2)
+
+
+def cost_importance(x, means, D, O, temperature):
+    """tau * x^T P mu, P given by its per-DoF blocks."""
+    b = _prior.precision_times(D, O, means)          # [NP, T, d]
+    return temperature * (x * b[:, None]).sum((-1, -2))

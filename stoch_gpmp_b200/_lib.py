@@ -1,0 +1,107 @@
+"""ctypes binding of include/stoch_gpmp_b200.h (libsgpmp.so, built in-tree by stoch_gpmp_b200.build).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+SGPMP_F32, SGPMP_F64 = 0, 1
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, 1, 2, 3, 4
+TABLE_STRIDE = 16
+MAX_FRAMES = 16
+MAX_SPHERES = 16
+NUM_TERMS = 5
+TERM_NAMES = ("start", "gp", "goal", "coll", "is")
+ABI_VERSION = 1
+
+
+class Shape(C.Structure):
+    _fields_ = [("B", C.c_int32), ("G", C.c_int32), ("K", C.c_int32), ("S", C.c_int32), ("T", C.c_int32),
+                ("n_dof", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32), ("problem_gid0", C.c_int64)]
+
+
+class CostDesc(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("sigma_start", C.c_double), ("sigma_gp", C.c_double),
+        ("sigma_goal_prior", C.c_double), ("temperature", C.c_double),
+        ("start", C.c_void_p), ("goals", C.c_void_p),
+        ("occ_map", C.c_void_p), ("map_of_problem", C.c_void_p),
+        ("n_maps", C.c_int32), ("map_h", C.c_int32), ("map_w", C.c_int32),
+        ("origin_xi", C.c_int32), ("origin_yi", C.c_int32), ("reserved0", C.c_int32),
+        ("map_inv_cell", C.c_double), ("map_sigma_coll", C.c_double),
+        ("spheres", C.c_void_p), ("n_spheres", C.c_int32), ("spheres_per_problem", C.c_int32),
+        ("sphere_sigma_coll", C.c_double),
+        ("n_frames", C.c_int32), ("include_base", C.c_int32),
+        ("chain_R", (C.c_double * 9) * MAX_FRAMES), ("chain_p", (C.c_double * 3) * MAX_FRAMES),
+        ("chain_joint", C.c_int32 * MAX_FRAMES),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/stoch_gpmp_b200.h declares
+_vp, _i32, _i64, _u32, _u64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+_SP, _DP = C.POINTER(Shape), C.POINTER(CostDesc)
+SIGNATURES = {
+    "sgpmp_abi_version": (C.c_int, []),
+    "sgpmp_last_error": (C.c_char_p, []),
+    "sgpmp_dof_supported": (C.c_int, [_i32]),
+    "sgpmp_launch_count": (_i64, []),
+    "sgpmp_prior_factor": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "sgpmp_prior_dense_L": (C.c_int, [_i32, _i32, _vp, _i32, _vp, _vp]),
+    "sgpmp_sample": (C.c_int, [_SP, _vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp]),
+    "sgpmp_cost": (C.c_int, [_SP, _DP, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgpmp_fk_link_positions": (C.c_int, [_DP, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "sgpmp_update": (C.c_int, [_SP, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgpmp_iterate": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgpmp_local_stats": (C.c_int, [_SP, _dbl, _vp, _vp, _vp, _vp]),
+    "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class SgpmpError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load libsgpmp.so (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            "stoch_gpmp_b200: CUDA library %s is missing — build it with `python -m stoch_gpmp_b200.build` "
+            "(needs nvcc; there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sgpmp_abi_version() != ABI_VERSION:
+        raise ImportError("stoch_gpmp_b200: %s has ABI %d, binding expects %d — rebuild"
+                          % (path, lib.sgpmp_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    """Translate a status code into the exception class the reference would raise."""
+    if rc == OK:
+        return
+    msg = load().sgpmp_last_error().decode(errors="replace")
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError("%s: %s" % (what, msg))
+    if rc == ERR_INVALID_ARG:
+        raise ValueError("%s: %s" % (what, msg))
+    raise SgpmpError("%s: status %d: %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(load().sgpmp_launch_count())

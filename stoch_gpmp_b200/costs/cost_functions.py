@@ -1,0 +1,263 @@
+"""Cost objects with the reference's constructor signatures (stoch_gpmp/costs/cost_functions.py).
+
+Here they are PARAMETER CARRIERS: `StochGPMP` lowers `CostComposite.cost_list` into the POD descriptor
+`sgpmp_cost_desc_t` consumed by the fused CUDA kernel (csrc/sgpmp_cost.cuh).  `eval()` is kept for
+drop-in use and runs the standalone CUDA cost kernel (K3); anything that cannot be lowered raises
+NotImplementedError — there is no CPU fallback.
+
+  CostGP          <- cost_functions.py:88-146     CostGoalPrior <- cost_functions.py:340-388
+  CostCollision   <- cost_functions.py:221-261    CostComposite <- cost_functions.py:32-58
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .. import ops
+from ..envs.occupancy import ObstacleMap
+from ..robots.serial_chain import SerialChainFK
+from .fields import LinkDistanceField
+
+
+class Cost:
+    def __init__(self, n_dof, traj_len):
+        self.n_dof = n_dof
+        self.dim = 2 * n_dof
+        self.traj_len = traj_len
+
+    def __call__(self, trajs, **observation):
+        return self.eval(trajs, **observation)
+
+    def eval(self, trajs, **observation):
+        """Evaluate this term alone through the CUDA cost kernel (trajs [..., T, d] on a CUDA device)."""
+        comp = CostComposite(self.n_dof, self.traj_len, [self], FK=observation.pop('FK', None))
+        return comp._eval_terms(trajs, **observation)[self._term]
+
+    def get_linear_system(self, trajs, **observation):
+        raise NotImplementedError("get_linear_system belongs to the Gauss-Newton GPMP planner, which is outside the "
+                                  "StochGPMP hot path (SURVEY §8f rank 4)")
+
+
+class CostGP(Cost):
+    """Start-state + GP transition factors.  start_state may be [d] or, for a problem batch, [B, d]."""
+    _term = 'gp+start'
+
+    def __init__(self, n_dof, traj_len, start_state, dt, sigma_params, tensor_args, **kwargs):
+        super().__init__(n_dof, traj_len)
+        self.start_state = start_state
+        self.dt = dt
+        self.sigma_start = sigma_params['sigma_start']
+        self.sigma_gp = sigma_params['sigma_gp']
+        self.tensor_args = tensor_args
+
+
+class CostGoalPrior(Cost):
+    """Goal-state factor per goal.  multi_goal_states [G, d] or [B, G, d]."""
+    _term = 'goal'
+
+    def __init__(self, n_dof, traj_len, multi_goal_states=None, num_particles_per_goal=None, num_samples=None,
+                 sigma_goal_prior=None, tensor_args=None):
+        super().__init__(n_dof, traj_len)
+        self.multi_goal_states = multi_goal_states
+        self.num_goals = multi_goal_states.shape[-2]
+        self.num_particles_per_goal = num_particles_per_goal
+        self.num_particles = num_particles_per_goal * self.num_goals
+        self.num_samples = num_samples
+        self.sigma_goal_prior = sigma_goal_prior
+        self.tensor_args = tensor_args
+
+
+class CostCollision(Cost):
+    """Obstacle factor over time steps 1..T-1.  field: ObstacleMap (or a list of them, one per problem of a
+    batch) or LinkDistanceField('rbf'); None disables the term as in the reference."""
+    _term = 'coll'
+
+    def __init__(self, n_dof, traj_len, field=None, sigma_coll=None, tensor_args=None):
+        super().__init__(n_dof, traj_len)
+        self.field = field
+        self.sigma_coll = sigma_coll
+        self.tensor_args = tensor_args
+
+
+class CostGoal(Cost):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("CostGoal (EE SE(3) goal field) is outside the round-1 hot path (SURVEY §8f rank 2)")
+
+
+class CostGPTrajectory(Cost):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("CostGPTrajectory is outside the StochGPMP hot path (SURVEY §8a-4)")
+
+
+class LoweredCost:
+    """Device-resident form of a CostComposite for a batch of B problems."""
+
+    def __init__(self, composite, B, G, device, dtype):
+        self.B, self.G, self.device, self.dtype = B, G, device, dtype
+        gp = goal = coll = None
+        for c in composite.cost_list:
+            if isinstance(c, CostGP):
+                if gp is not None:
+                    raise NotImplementedError("more than one CostGP in cost_list")
+                gp = c
+            elif isinstance(c, CostGoalPrior):
+                if goal is not None:
+                    raise NotImplementedError("more than one CostGoalPrior in cost_list")
+                goal = c
+            elif isinstance(c, CostCollision):
+                if c.field is None:
+                    continue                      # the reference returns 0 for a field-less collision cost
+                if coll is not None:
+                    raise NotImplementedError("more than one collision field in cost_list (SURVEY §8f rank 1)")
+                coll = c
+            else:
+                raise NotImplementedError("cost object %s cannot be lowered to the CUDA path (no CPU fallback)"
+                                          % type(c).__name__)
+        if gp is None:
+            raise NotImplementedError("cost_list needs a CostGP (start + GP factors)")
+        n, d = composite.n_dof, 2 * composite.n_dof
+        self.n_dof, self.T = n, composite.traj_len
+        kw = dict(device=device, dtype=dtype)
+        self.dt, self.sigma_start, self.sigma_gp = float(gp.dt), float(gp.sigma_start), float(gp.sigma_gp)
+        self.start = torch.as_tensor(gp.start_state).to(**kw).reshape(-1, d).expand(B, d).contiguous()
+        self.goals, self.sigma_goal_prior = None, -1.0
+        self.goal_K = self.goal_S = None
+        if goal is not None:
+            self.goals = torch.as_tensor(goal.multi_goal_states).to(**kw).reshape(-1, G, d).expand(B, G, d).contiguous()
+            self.sigma_goal_prior = float(goal.sigma_goal_prior)
+            self.goal_K, self.goal_S = goal.num_particles_per_goal, goal.num_samples
+        self.map = self.map_index = None
+        self.map_meta = None
+        self.sphere_sigma = None
+        self.fk = None
+        if coll is not None:
+            fields = coll.field if isinstance(coll.field, (list, tuple)) else [coll.field]
+            if all(isinstance(f, ObstacleMap) for f in fields):
+                f0 = fields[0]
+                for f in fields:
+                    if f.map.shape != f0.map.shape or f.cell_size != f0.cell_size:
+                        raise NotImplementedError("all occupancy maps of a batch must share shape and cell size")
+                if len(fields) not in (1, B):
+                    raise ValueError("need 1 or B=%d occupancy maps, got %d" % (B, len(fields)))
+                if f0.map.shape[0] != f0.map.shape[1]:
+                    raise NotImplementedError("non-square occupancy maps are not supported (obst_map.py:177-178 clamps "
+                                              "x with shape[0] and y with shape[1])")
+                import numpy as np
+                self.map = torch.as_tensor(np.stack([f.map for f in fields])).to(**kw).contiguous()
+                if len(fields) == B and B > 1:
+                    self.map_index = torch.arange(B, dtype=torch.int32, device=device)
+                # 1/cell_size as the reference forms it: X * (1/self.cell_size) (obst_map.py:172)
+                self.map_meta = dict(h=f0.map.shape[0], w=f0.map.shape[1], oxi=f0.origin_xi, oyi=f0.origin_yi,
+                                     inv_cell=1.0 / f0.cell_size, sigma=float(coll.sigma_coll))
+            elif len(fields) == 1 and isinstance(fields[0], LinkDistanceField):
+                fields[0].check_lowerable()
+                if not isinstance(composite.FK, SerialChainFK):
+                    raise NotImplementedError(
+                        "LinkDistanceField needs CostComposite(FK=<stoch_gpmp_b200.robots.SerialChainFK>), e.g. PandaFK(); "
+                        "arbitrary FK callables cannot be lowered to the CUDA kernel")
+                self.fk = composite.FK
+                if self.fk.n_dofs != n:
+                    raise ValueError("FK chain has %d joints but n_dof=%d" % (self.fk.n_dofs, n))
+                if len(self.fk.joint) > _lib.MAX_FRAMES:
+                    raise NotImplementedError("FK chain longer than %d frames" % _lib.MAX_FRAMES)
+                self.sphere_sigma = float(coll.sigma_coll)
+            else:
+                raise NotImplementedError("collision field %s cannot be lowered to the CUDA path"
+                                          % type(fields[0]).__name__)
+        self._spheres = None
+
+    def desc(self, temperature, obstacle_spheres=None):
+        """Fill an sgpmp_cost_desc_t (keeps the tensors it points to alive on self)."""
+        d = _lib.CostDesc()
+        d.dt, d.sigma_start, d.sigma_gp = self.dt, self.sigma_start, self.sigma_gp
+        d.sigma_goal_prior = self.sigma_goal_prior
+        d.temperature = float(temperature)
+        d.start = self.start.data_ptr()
+        d.goals = self.goals.data_ptr() if self.goals is not None else None
+        if self.map is not None:
+            m = self.map_meta
+            d.occ_map = self.map.data_ptr()
+            d.map_of_problem = self.map_index.data_ptr() if self.map_index is not None else None
+            d.n_maps, d.map_h, d.map_w = self.map.shape[0], m['h'], m['w']
+            d.origin_xi, d.origin_yi = m['oxi'], m['oyi']
+            d.map_inv_cell, d.map_sigma_coll = m['inv_cell'], m['sigma']
+        if self.fk is not None:
+            if obstacle_spheres is None:
+                # reference: LinkDistanceField.compute_cost returns 0 without spheres (fields.py:64-65)
+                d.spheres = None
+            else:
+                sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
+                if sp.dim() == 2:
+                    sp = sp.unsqueeze(0)
+                if sp.shape[0] not in (1, self.B) or sp.shape[-1] != 4:
+                    raise ValueError("obstacle_spheres must be [1,O,4] or [B,O,4], got %s" % (tuple(sp.shape),))
+                if sp.shape[1] > _lib.MAX_SPHERES:
+                    raise NotImplementedError("more than %d obstacle spheres" % _lib.MAX_SPHERES)
+                self._spheres = sp.contiguous()
+                d.spheres = self._spheres.data_ptr()
+                d.n_spheres = sp.shape[1]
+                d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
+                d.sphere_sigma_coll = self.sphere_sigma
+                fk = self.fk
+                d.n_frames = len(fk.joint)
+                d.include_base = 1 if fk.include_base else 0
+                for f in range(len(fk.joint)):
+                    for k in range(9):
+                        d.chain_R[f][k] = fk.R[f][k]
+                    for k in range(3):
+                        d.chain_p[f][k] = fk.xyz[f][k]
+                    d.chain_joint[f] = fk.joint[f]
+        return d
+
+
+class CostComposite(Cost):
+
+    def __init__(self, n_dof, traj_len, cost_list, FK=None, tensor_args=None):
+        super().__init__(n_dof, traj_len)
+        self.cost_list = cost_list
+        self.FK = FK
+        self.tensor_args = tensor_args
+
+    def lower(self, B, G, device, dtype):
+        return LoweredCost(self, B, G, device, dtype)
+
+    def _eval_terms(self, trajs, **observation):
+        if not trajs.is_cuda:
+            raise RuntimeError("cost.eval: trajs is on %s — CUDA only, no CPU fallback" % trajs.device)
+        T, d = self.traj_len, self.dim
+        x = trajs.reshape(-1, T, d)
+        nb = x.shape[0]
+        goal = next((c for c in self.cost_list if isinstance(c, CostGoalPrior)), None)
+        if goal is not None:
+            G, K, S = goal.num_goals, goal.num_particles_per_goal, goal.num_samples
+            if G * K * S != nb:
+                raise RuntimeError("CostGoalPrior was built for %d x %d x %d trajectories, got %d" % (G, K, S, nb))
+        else:
+            G, K, S = 1, 1, nb
+        low = self.lower(1, G, x.device, x.dtype)
+        shape = ops.make_shape(1, G, K, S, T, self.n_dof, x.dtype)
+        xs = x.reshape(1, G * K, S, T, d).permute(0, 1, 3, 4, 2).contiguous()
+        desc = low.desc(0.0, observation.get('obstacle_spheres', None))
+        costs, terms = ops.cost(shape, desc, None, xs, None, want_terms=True)
+        out = {nm: terms[i].reshape(-1) for i, nm in enumerate(_lib.TERM_NAMES)}
+        out['gp+start'] = out['start'] + out['gp']
+        out['total'] = costs.reshape(-1)
+        return out
+
+    def eval(self, trajs, **observation):
+        return self._eval_terms(trajs, **observation)['total']
+
+
+def _map_lookup_cuda(obst_map, X):
+    """ObstacleMap.compute_cost through the cost kernel: a 2-step, 1-DoF-pair 'trajectory' per point whose
+    collision term is exactly the lookup at the point."""
+    if not X.is_cuda:
+        raise RuntimeError("ObstacleMap.compute_cost: X is on %s — CUDA only, no CPU fallback" % X.device)
+    pts = X.reshape(-1, 2)
+    n = pts.shape[0]
+    traj = torch.zeros(n, 2, 4, dtype=pts.dtype, device=pts.device)
+    traj[:, 1, :2] = pts
+    ta = dict(device=pts.device, dtype=pts.dtype)
+    comp = CostComposite(2, 2, [CostGP(2, 2, torch.zeros(4, **ta), 1.0, dict(sigma_start=1.0, sigma_gp=1.0), ta),
+                                CostCollision(2, 2, field=obst_map, sigma_coll=1.0)])
+    return comp._eval_terms(traj)['coll'].reshape(X.shape[:-1])

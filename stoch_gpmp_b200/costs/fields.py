@@ -1,0 +1,39 @@
+"""Distance fields (parameter carriers).  Mirrors stoch_gpmp/costs/fields.py for the variants on the
+StochGPMP hot path: LinkDistanceField with field_type='rbf' and no link interpolation
+(costs/fields.py:30-79).  The arithmetic runs in csrc/sgpmp_cost.cuh::link_sphere_rbf."""
+
+
+class DistanceField:
+    def __init__(self, tensor_args=None):
+        self.tensor_args = tensor_args
+
+    def zero_grad(self):
+        pass
+
+
+class LinkDistanceField(DistanceField):
+    """sum over link frames and obstacle spheres of exp(-0.5 |p - c|^2 / r^2)."""
+
+    def __init__(self, field_type='rbf', clamp_sdf=False, num_interpolate=0, link_interpolate_range=(5, 7), **kwargs):
+        super().__init__(**kwargs)
+        self.field_type = field_type
+        self.clamp_sdf = clamp_sdf
+        self.num_interpolate = num_interpolate
+        self.link_interpolate_range = list(link_interpolate_range)
+
+    def check_lowerable(self):
+        if self.field_type != 'rbf':
+            raise NotImplementedError("LinkDistanceField(field_type=%r): only 'rbf' is lowered to the CUDA path "
+                                      "(SURVEY §8f rank 3)" % (self.field_type,))
+        if self.num_interpolate:
+            raise NotImplementedError("LinkDistanceField(num_interpolate>0) is not lowered yet (SURVEY §8f rank 1)")
+
+
+class LinkSelfDistanceField(DistanceField):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("LinkSelfDistanceField is outside the round-1 hot path (SURVEY §8f rank 1); no CPU fallback")
+
+
+class EESE3DistanceField(DistanceField):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("EESE3DistanceField needs torch_robotics' SE3_distance (absent); SURVEY §8f rank 2")

@@ -1,0 +1,271 @@
+// K3 — standalone per-trajectory-sample cost kernel, and the host-side lowering of sgpmp_cost_desc_t.
+// (Arithmetic and reference citations: sgpmp_cost.cuh.)
+//
+// Mapping: one thread per trajectory sample marching over t; the S-minor sample layout makes the 2n
+// loads of a step fully coalesced across the warp.  Per-particle constants (start, goal, b = P mu,
+// sphere table) are staged in shared memory once per CTA.
+#include <math.h>
+
+#include "sgpmp_common.cuh"
+#include "sgpmp_cost.cuh"
+
+namespace sgpmp {
+
+template <typename real>
+int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostParams<real>& o) {
+    memset(&o, 0, sizeof(o));
+    if (!(d.dt > 0) || !(d.sigma_start > 0) || !(d.sigma_gp > 0) || !d.start) {
+        set_error("cost desc: dt, sigma_start, sigma_gp must be > 0 and start non-null");
+        return SGPMP_ERR_INVALID_ARG;
+    }
+    o.dt = (real)d.dt;
+    o.inv_sig_start2 = (real)(1.0 / (d.sigma_start * d.sigma_start));
+    // Q^-1 blocks exactly as GPFactor.calc_Q_inv forms them (gp_factor.py:44-52)
+    const double qc = 1.0 / (d.sigma_gp * d.sigma_gp);
+    o.q11 = (real)(12.0 * pow(d.dt, -3.0) * qc);
+    o.q12x2 = (real)(2.0 * (-6.0 * pow(d.dt, -2.0) * qc));
+    o.q22 = (real)(4.0 * pow(d.dt, -1.0) * qc);
+    o.temperature = (real)d.temperature;
+    o.start = (const real*)d.start;
+    o.goals = (const real*)d.goals;
+    o.has_goal = (d.goals != nullptr && d.sigma_goal_prior > 0) ? 1 : 0;
+    o.inv_sig_goal2 = o.has_goal ? (real)(1.0 / (d.sigma_goal_prior * d.sigma_goal_prior)) : (real)0;
+    o.has_map = d.occ_map != nullptr;
+    o.has_spheres = d.spheres != nullptr && d.n_spheres > 0;
+    if (o.has_map && o.has_spheres) {
+        set_error("cost desc: one collision field per problem batch (map or spheres), got both");
+        return SGPMP_ERR_UNSUPPORTED;
+    }
+    if (o.has_map) {
+        if (d.map_h <= 0 || d.map_w <= 0 || d.n_maps <= 0 || !(d.map_sigma_coll > 0)) {
+            set_error("cost desc: bad occupancy-map parameters");
+            return SGPMP_ERR_INVALID_ARG;
+        }
+        if (d.map_h != d.map_w) {
+            set_error("cost desc: non-square occupancy maps are not supported (the reference's clamp "
+                      "obst_map.py:177-178 is only well defined for square maps)");
+            return SGPMP_ERR_UNSUPPORTED;
+        }
+        if (sh.n_dof < 2) { set_error("cost desc: occupancy map needs n_dof >= 2"); return SGPMP_ERR_INVALID_ARG; }
+        o.occ_map = (const real*)d.occ_map;
+        o.map_of_problem = d.map_of_problem;
+        o.map_h = d.map_h; o.map_w = d.map_w; o.n_maps = d.n_maps;
+        o.origin_xi = d.origin_xi; o.origin_yi = d.origin_yi;
+        o.map_inv_cell = (real)d.map_inv_cell;
+        o.map_origin_x = (real)d.origin_xi;
+        o.map_origin_y = (real)d.origin_yi;
+        o.map_w_coll = (real)(1.0 / (d.map_sigma_coll * d.map_sigma_coll));
+    }
+    if (o.has_spheres) {
+        if (d.n_spheres > SGPMP_MAX_SPHERES || !(d.sphere_sigma_coll > 0)) {
+            set_error("cost desc: n_spheres must be <= %d and sigma_coll > 0", SGPMP_MAX_SPHERES);
+            return SGPMP_ERR_INVALID_ARG;
+        }
+        if (d.n_frames < sh.n_dof || d.n_frames > SGPMP_MAX_FRAMES) {
+            set_error("cost desc: FK chain needs n_dof <= n_frames <= %d", SGPMP_MAX_FRAMES);
+            return SGPMP_ERR_INVALID_ARG;
+        }
+        for (int f = 0; f < d.n_frames; ++f) {
+            const int want = f < sh.n_dof ? f : -1;
+            if (d.chain_joint[f] != want) {
+                set_error("cost desc: FK chain must be a serial arm: frames 0..n_dof-1 revolute-z with joint f, "
+                          "then fixed frames (frame %d has joint %d)", f, d.chain_joint[f]);
+                return SGPMP_ERR_UNSUPPORTED;
+            }
+        }
+        o.spheres = (const real*)d.spheres;
+        o.n_spheres = d.n_spheres;
+        o.spheres_per_problem = d.spheres_per_problem;
+        o.sphere_w_coll = (real)(1.0 / (d.sphere_sigma_coll * d.sphere_sigma_coll));
+        o.n_frames = d.n_frames;
+        o.include_base = d.include_base;
+        for (int f = 0; f < d.n_frames; ++f) {
+            for (int k = 0; k < 9; ++k) o.R[f][k] = (real)d.chain_R[f][k];
+            for (int k = 0; k < 3; ++k) o.p[f][k] = (real)d.chain_p[f][k];
+            o.joint[f] = d.chain_joint[f];
+        }
+    }
+    return SGPMP_OK;
+}
+template int lower_cost_desc<float>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<float>&);
+template int lower_cost_desc<double>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<double>&);
+
+template <typename real, int N>
+__global__ void __launch_bounds__(128)
+cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int T,
+            const double* __restrict__ tab, const real* __restrict__ samples, const real* __restrict__ means,
+            real* __restrict__ costs, real* __restrict__ terms, size_t term_stride) {
+    constexpr int d = 2 * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tabDO = reinterpret_cast<double*>(smem_raw);                 // [T][7]
+    real* bvec = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]
+    real* mu = bvec + (size_t)T * d;                                     // [T][d]
+    real* start = mu + (size_t)T * d;                                    // [d]
+    real* goal = start + d;                                              // [d]
+    real* sph = goal + d;                                                // [O][4]
+
+    const int NP = G * K;
+    const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
+    if (means)
+        for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
+            tabDO[k] = tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + SGPMP_TAB_D11 + (k % 7)];
+    if (means)
+        for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        start[k] = P.start[(size_t)b * d + k];
+        goal[k] = P.has_goal ? P.goals[((size_t)b * G + p / K) * d + k] : (real)0;
+    }
+    if (P.has_spheres)
+        for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x) {
+            const real* s4 = P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4;
+            sph[4 * k + 0] = s4[0]; sph[4 * k + 1] = s4[1]; sph[4 * k + 2] = s4[2];
+            const real r = s4[3];
+            sph[4 * k + 3] = (sizeof(real) == 4) ? (real)(-0.5 * 1.4426950408889634 / ((double)r * (double)r))
+                                                 : (real)(-0.5 / ((double)r * (double)r));
+        }
+    __syncthreads();
+    if (means) {
+        for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
+            const int t = k / N, i = k - t * N;
+            precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * d + i], &bvec[t * d + N + i]);
+        }
+    }
+    __syncthreads();
+
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    CostSmem<real> sm;
+    sm.start = start; sm.goal = goal; sm.bvec = means ? bvec : nullptr; sm.sph = sph;
+    sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+
+    TrajCost<real, N> tc;
+    tc.begin();
+    const real* xs = samples + (size_t)bp * T * d * S + s;
+    for (int t = 0; t < T; ++t) {
+        real x[d];
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] = xs[((size_t)t * d + j) * S];
+        tc.step(P, sm, t, T, x);
+    }
+    tc.finish(P);
+    const size_t o = (size_t)bp * S + s;
+    costs[o] = tc.total();
+    if (terms) {
+        terms[SGPMP_TERM_START * term_stride + o] = tc.c_start;
+        terms[SGPMP_TERM_GP * term_stride + o] = tc.c_gp;
+        terms[SGPMP_TERM_GOAL * term_stride + o] = tc.c_goal;
+        terms[SGPMP_TERM_COLL * term_stride + o] = tc.c_coll;
+        terms[SGPMP_TERM_IS * term_stride + o] = tc.c_is;
+    }
+}
+
+// Link-frame origins of N_cfg configurations: q [n_cfg][N] -> pos [n_cfg][L][3].  Same FK code as the cost
+// kernel; used for known-answer tests and collision-freeness checks of final plans.
+template <typename real, int N>
+__global__ void fk_links_kernel(const __grid_constant__ CostParams<real> P, int n_cfg, const real* __restrict__ q,
+                                real* __restrict__ pos) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cfg) return;
+    real qq[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) qq[i] = q[(size_t)c * N + i];
+    const int L = P.n_frames + (P.include_base ? 1 : 0);
+    real* out = pos + (size_t)c * L * 3;
+    int l = 0;
+    fk_visit_links<real, N>(P, qq, [&](real x, real y, real z) {
+        out[3 * l + 0] = x; out[3 * l + 1] = y; out[3 * l + 2] = z;
+        ++l;
+    });
+}
+
+template <typename real>
+static int launch_fk(const sgpmp_cost_desc_t& desc, int n_dof, int n_cfg, const void* q, void* pos, cudaStream_t st) {
+    sgpmp_shape_t sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.n_dof = n_dof;
+    CostParams<real> P;
+    memset(&P, 0, sizeof(P));
+    if (desc.n_frames < n_dof || desc.n_frames > SGPMP_MAX_FRAMES) { set_error("sgpmp_fk_link_positions: bad n_frames"); return SGPMP_ERR_INVALID_ARG; }
+    for (int f = 0; f < desc.n_frames; ++f) {
+        if (desc.chain_joint[f] != (f < n_dof ? f : -1)) { set_error("sgpmp_fk_link_positions: chain is not a serial arm"); return SGPMP_ERR_UNSUPPORTED; }
+        for (int k = 0; k < 9; ++k) P.R[f][k] = (real)desc.chain_R[f][k];
+        for (int k = 0; k < 3; ++k) P.p[f][k] = (real)desc.chain_p[f][k];
+    }
+    P.n_frames = desc.n_frames;
+    P.include_base = desc.include_base;
+    const int bs = 128;
+    switch (n_dof) {
+#define SGPMP_DOF_CASE(N) case N: fk_links_kernel<real, N><<<(n_cfg + bs - 1) / bs, bs, 0, st>>>(P, n_cfg, (const real*)q, (real*)pos); break;
+#include "sgpmp_dof_list.inc"
+#undef SGPMP_DOF_CASE
+        default:
+            set_error("sgpmp_fk_link_positions: n_dof=%d is not instantiated", n_dof);
+            return SGPMP_ERR_UNSUPPORTED;
+    }
+    SGPMP_CHECK_LAUNCH("sgpmp_fk_link_positions");
+    return SGPMP_OK;
+}
+
+template <typename real, int N>
+static int launch_cost_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
+                         const void* means, void* costs, void* terms, cudaStream_t st) {
+    const int NP = sh.G * sh.K, d = 2 * N, bs = 128;
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)2 * sh.T * d + 2 * d + 4 * SGPMP_MAX_SPHERES) * sizeof(real);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) { set_error("sgpmp_cost: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
+        cudaFuncSetAttribute(cost_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    cost_kernel<real, N><<<grid, bs, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
+                                                  (const real*)means, (real*)costs, (real*)terms,
+                                                  (size_t)sh.B * NP * sh.S);
+    SGPMP_CHECK_LAUNCH("sgpmp_cost");
+    return SGPMP_OK;
+}
+
+template <typename real>
+static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
+                       const void* means, void* costs, void* terms, cudaStream_t st) {
+    CostParams<real> P;
+    int rc = lower_cost_desc<real>(sh, desc, P);
+    if (rc != SGPMP_OK) return rc;
+    switch (sh.n_dof) {
+#define SGPMP_DOF_CASE(N) case N: return launch_cost_n<real, N>(sh, P, tables, samples, means, costs, terms, st);
+#include "sgpmp_dof_list.inc"
+#undef SGPMP_DOF_CASE
+        default:
+            set_error("sgpmp_cost: n_dof=%d is not instantiated (see sgpmp_dof_list.inc)", sh.n_dof);
+            return SGPMP_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace sgpmp
+
+using namespace sgpmp;
+
+extern "C" int sgpmp_dof_supported(int32_t n_dof) {
+    switch (n_dof) {
+#define SGPMP_DOF_CASE(N) case N: return 1;
+#include "sgpmp_dof_list.inc"
+#undef SGPMP_DOF_CASE
+        default: return 0;
+    }
+}
+
+extern "C" int sgpmp_cost(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+                          const void* samples, const void* means, void* costs, void* terms, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_cost: invalid shape");
+    SGPMP_REQUIRE(desc && samples && costs, "sgpmp_cost: null pointer");
+    SGPMP_REQUIRE(tables || !means, "sgpmp_cost: the IS term (means != NULL) needs the prior tables");
+    if (shape->dtype == SGPMP_F32)
+        return launch_cost<float>(*shape, *desc, tables, samples, means, costs, terms, (cudaStream_t)stream);
+    return launch_cost<double>(*shape, *desc, tables, samples, means, costs, terms, (cudaStream_t)stream);
+}
+
+extern "C" int sgpmp_fk_link_positions(const sgpmp_cost_desc_t* desc, int32_t n_dof, int32_t dtype, int32_t n_cfg,
+                                       const void* q, void* pos, void* stream) {
+    SGPMP_REQUIRE(desc && q && pos && n_cfg > 0 && n_dof > 0, "sgpmp_fk_link_positions: bad arguments");
+    SGPMP_REQUIRE(dtype == SGPMP_F32 || dtype == SGPMP_F64, "sgpmp_fk_link_positions: bad dtype");
+    if (dtype == SGPMP_F32) return launch_fk<float>(*desc, n_dof, n_cfg, q, pos, (cudaStream_t)stream);
+    return launch_fk<double>(*desc, n_dof, n_cfg, q, pos, (cudaStream_t)stream);
+}

@@ -1,0 +1,102 @@
+// K2 — trajectory sampling x = mu + L eps as a banded recurrence.
+//
+// Reference being replaced: MultiMPPrior.sample (mp_priors_multi.py:204-207) ->
+// MultivariateNormal.rsample (multivariate_normal.py:251-254): eps = normal(S,NP,M);
+// loc + L @ eps with a dense M x M L per particle (2 NP S M^2 flop, 84-91 % of the reference's
+// iteration).  L^-1 is block-bidiagonal, so  y_t = G_t eps_t - H_t y_{t-1}  (16 flop per state).
+//
+// Mapping: one thread per (sample, DoF); the S-minor layout [B,NP,T,d,S] makes every load/store of a
+// warp one contiguous 128-byte (fp32) line.  The G/H tables (7 reals per step) sit in shared memory.
+#include "sgpmp_common.cuh"
+#include "sgpmp_rng.cuh"
+
+namespace sgpmp {
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, const double* __restrict__ tab,
+              const real* __restrict__ means, const real* __restrict__ eps_in, RngKey key,
+              real* __restrict__ samples, real* __restrict__ eps_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* gh = reinterpret_cast<real*>(smem_raw);   // [T][7]
+    for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
+        gh[k] = (real)tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + (k % 7)];
+    __syncthreads();
+
+    const int bp = blockIdx.x;                       // flat (problem, particle)
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= S * n) return;
+    const int i = idx / S, s = idx - i * S;
+    const int d = 2 * n;
+    const size_t base = (size_t)bp * T * d * S;      // samples / eps
+    const real* mu = means + (size_t)bp * T * d;
+    const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
+
+    real yp = 0, yv = 0;
+    for (int tp = 0; tp < (T + 1) / 2; ++tp) {
+        real e[4];
+        if (eps_in) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * tp + h;
+                if (t < T) {
+                    e[2 * h] = eps_in[base + ((size_t)t * d + i) * S + s];
+                    e[2 * h + 1] = eps_in[base + ((size_t)t * d + n + i) * S + s];
+                } else {
+                    e[2 * h] = e[2 * h + 1] = 0;
+                }
+            }
+        } else {
+            normal4<real>(key, tp, i, s, pgid, e[0], e[1], e[2], e[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * tp + h;
+            if (t < T) {
+                const real* r = gh + t * 7;
+                const real np_ = r[0] * e[2 * h] - (r[3] * yp + r[4] * yv);
+                const real nv_ = r[1] * e[2 * h] + r[2] * e[2 * h + 1] - (r[5] * yp + r[6] * yv);
+                yp = np_; yv = nv_;
+                const size_t op = base + ((size_t)t * d + i) * S + s;
+                const size_t ov = base + ((size_t)t * d + n + i) * S + s;
+                samples[op] = mu[t * d + i] + yp;
+                samples[ov] = mu[t * d + n + i] + yv;
+                if (eps_out) { eps_out[op] = e[2 * h]; eps_out[ov] = e[2 * h + 1]; }
+            }
+        }
+    }
+}
+
+template <typename real>
+static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
+                         uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st) {
+    const int NP = sh.G * sh.K;
+    const int bs = 256;
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S * sh.n_dof + bs - 1) / bs));
+    const size_t smem = (size_t)sh.T * 7 * sizeof(real);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) { set_error("sgpmp_sample: T=%d too large for the shared-memory tables", sh.T); return SGPMP_ERR_UNSUPPORTED; }
+        cudaFuncSetAttribute(sample_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
+    sample_kernel<real><<<grid, bs, smem, st>>>(NP, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NP, tables,
+                                                (const real*)means, (const real*)eps_in, key, (real*)samples,
+                                                (real*)eps_out);
+    SGPMP_CHECK_LAUNCH("sgpmp_sample");
+    return SGPMP_OK;
+}
+
+}  // namespace sgpmp
+
+using namespace sgpmp;
+
+extern "C" int sgpmp_sample(const sgpmp_shape_t* shape, const double* tables, const void* means,
+                            const void* eps_in, uint64_t seed, uint32_t draw, void* samples, void* eps_out,
+                            void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_sample: invalid shape");
+    SGPMP_REQUIRE(tables && means && samples, "sgpmp_sample: null pointer");
+    SGPMP_REQUIRE((int64_t)shape->B * shape->G * shape->K <= 0x7fffffffLL, "sgpmp_sample: too many particles for one launch");
+    if (shape->dtype == SGPMP_F32)
+        return launch_sample<float>(*shape, tables, means, eps_in, seed, draw, samples, eps_out, (cudaStream_t)stream);
+    return launch_sample<double>(*shape, tables, means, eps_in, seed, draw, samples, eps_out, (cudaStream_t)stream);
+}

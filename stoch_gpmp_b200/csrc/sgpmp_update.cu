@@ -1,0 +1,207 @@
+// K4 — per-particle softmax weights + weighted-mean update, and the split-particle statistics.
+//
+// Reference being replaced: StochGPMP._update_distribution (planner.py:263-275)
+//     w = softmax(-costs/tau, dim=1);  grad = sum_s w_s (x_s - mu);  mu += step_size * grad
+// (the set_mean() that follows, planner.py:273 -> mp_priors_multi.py:120-123, rebuilds the whole
+// MultivariateNormal — Cholesky + PD validation of NP dense MxM copies — although the precision never
+// changes; nothing of that remains here).
+//
+// Mapping: one CTA per (problem, particle).  Weights live in shared memory; each warp owns rows (t, j)
+// of the S-minor sample block and reduces over s with coalesced loads + shuffles.  HBM-bound: M*S reals
+// read per particle.
+#include "sgpmp_common.cuh"
+
+namespace sgpmp {
+
+// block-wide max / sum via warp shuffles + one shared-memory hop (red: >= 32 reals)
+template <typename real>
+__device__ __forceinline__ real block_max(real v, real* red) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    real r = red[0];
+    for (int k = 1; k < nw; ++k) r = sg_max(r, red[k]);
+    return r;
+}
+template <typename real>
+__device__ __forceinline__ real block_sum(real v, real* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    real r = 0;
+    for (int k = 0; k < nw; ++k) r += red[k];
+    return r;
+}
+
+// e_s = exp(-c_s/tau - m) into wsm[S]; returns (m, Z).  normalise=true divides by Z.
+template <typename real>
+__device__ __forceinline__ void block_softmax(const real* __restrict__ c, int S, real tau, real* wsm, real* red,
+                                              bool normalise, real* m_out, real* Z_out) {
+    real m = -INFINITY;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const real z = -c[s] / tau;
+        wsm[s] = z;
+        m = sg_max(m, z);
+    }
+    m = block_max(m, red);
+    real Z = 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const real e = sg_exp(wsm[s] - m);
+        wsm[s] = e;
+        Z += e;
+    }
+    Z = block_sum(Z, red);
+    if (normalise)
+        for (int s = threadIdx.x; s < S; s += blockDim.x) wsm[s] = wsm[s] / Z;
+    __syncthreads();
+    *m_out = m;
+    *Z_out = Z;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs, const real* __restrict__ samples,
+              real* __restrict__ means, real* __restrict__ grad, real* __restrict__ weights) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* wsm = reinterpret_cast<real*>(smem_raw);   // [S]
+    real* red = wsm + S;                             // [32]
+    const size_t bp = blockIdx.x;
+    real m, Z;
+    block_softmax<real>(costs + bp * S, S, tau, wsm, red, true, &m, &Z);
+    if (weights)
+        for (int s = threadIdx.x; s < S; s += blockDim.x) weights[bp * S + s] = wsm[s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const real* xs = samples + bp * (size_t)M * S;
+    for (int r = warp; r < M; r += nw) {
+        const real mu = means[bp * M + r];
+        real acc = 0;
+        for (int s = lane; s < S; s += 32) acc += wsm[s] * (xs[(size_t)r * S + s] - mu);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (grad) grad[bp * M + r] = acc;
+            means[bp * M + r] = mu + step * acc;
+        }
+    }
+}
+
+// split-particle mode: stats[bp] = (m, Z, A[M]),  A = sum_s exp(-c_s/tau - m) eps_s
+template <typename real>
+__global__ void __launch_bounds__(256)
+local_stats_kernel(int S, int M, real tau, const real* __restrict__ costs, const real* __restrict__ eps,
+                   real* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* wsm = reinterpret_cast<real*>(smem_raw);
+    real* red = wsm + S;
+    const size_t bp = blockIdx.x;
+    real m, Z;
+    block_softmax<real>(costs + bp * S, S, tau, wsm, red, false, &m, &Z);
+    real* out = stats + bp * (size_t)(M + 2);
+    if (threadIdx.x == 0) { out[0] = m; out[1] = Z; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const real* es = eps + bp * (size_t)M * S;
+    for (int r = warp; r < M; r += nw) {
+        real acc = 0;
+        for (int s = lane; s < S; s += 32) acc += wsm[s] * es[(size_t)r * S + s];
+        acc = warp_sum(acc);
+        if (lane == 0) out[2 + r] = acc;
+    }
+}
+
+// mu += step * L (A / Z): one thread per (particle, DoF) runs the banded recurrence over t.
+template <typename real>
+__global__ void apply_stats_kernel(int n_particles, int T, int n, const double* __restrict__ tab, real step,
+                                   const real* __restrict__ stats, real* __restrict__ means, real* __restrict__ grad) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_particles * n) return;
+    const int bp = idx / n, i = idx - bp * n;
+    const int d = 2 * n;
+    const size_t M = (size_t)T * d;
+    const real* st = stats + (size_t)bp * (M + 2);
+    const real invZ = (real)1 / st[1];
+    real yp = 0, yv = 0;
+    for (int t = 0; t < T; ++t) {
+        const double* r = tab + (size_t)t * SGPMP_TABLE_STRIDE;
+        const real ep = st[2 + t * d + i] * invZ, ev = st[2 + t * d + n + i] * invZ;
+        const real np_ = (real)r[SGPMP_TAB_G11] * ep - ((real)r[SGPMP_TAB_H11] * yp + (real)r[SGPMP_TAB_H12] * yv);
+        const real nv_ = (real)r[SGPMP_TAB_G21] * ep + (real)r[SGPMP_TAB_G22] * ev -
+                         ((real)r[SGPMP_TAB_H21] * yp + (real)r[SGPMP_TAB_H22] * yv);
+        yp = np_; yv = nv_;
+        const size_t op = (size_t)bp * M + t * d + i, ov = op + n;
+        if (grad) { grad[op] = yp; grad[ov] = yv; }
+        means[op] += step * yp;
+        means[ov] += step * yv;
+    }
+}
+
+template <typename real>
+static int launch_update(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples,
+                         void* means, void* grad, void* weights, cudaStream_t st) {
+    const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
+    const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(update_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    update_kernel<real><<<(unsigned)(sh.B * NP), 256, smem, st>>>(sh.S, M, (real)tau, (real)step, (const real*)costs,
+                                                                 (const real*)samples, (real*)means, (real*)grad,
+                                                                 (real*)weights);
+    SGPMP_CHECK_LAUNCH("sgpmp_update");
+    return SGPMP_OK;
+}
+
+template <typename real>
+static int launch_local_stats(const sgpmp_shape_t& sh, double tau, const void* costs, const void* eps, void* stats,
+                              cudaStream_t st) {
+    const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
+    const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(local_stats_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    local_stats_kernel<real><<<(unsigned)(sh.B * NP), 256, smem, st>>>(sh.S, M, (real)tau, (const real*)costs,
+                                                                      (const real*)eps, (real*)stats);
+    SGPMP_CHECK_LAUNCH("sgpmp_local_stats");
+    return SGPMP_OK;
+}
+
+template <typename real>
+static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats, void* means,
+                              void* grad, cudaStream_t st) {
+    const int n_particles = sh.B * sh.G * sh.K;
+    const int total = n_particles * sh.n_dof, bs = 128;
+    apply_stats_kernel<real><<<(total + bs - 1) / bs, bs, 0, st>>>(n_particles, sh.T, sh.n_dof, tables, (real)step,
+                                                                  (const real*)stats, (real*)means, (real*)grad);
+    SGPMP_CHECK_LAUNCH("sgpmp_apply_stats");
+    return SGPMP_OK;
+}
+
+}  // namespace sgpmp
+
+using namespace sgpmp;
+
+extern "C" int sgpmp_update(const sgpmp_shape_t* shape, double temperature, double step_size, const void* costs,
+                            const void* samples, void* means, void* grad, void* weights, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_update: invalid shape");
+    SGPMP_REQUIRE(costs && samples && means, "sgpmp_update: null pointer");
+    SGPMP_REQUIRE(temperature > 0, "sgpmp_update: temperature must be > 0");
+    if (shape->dtype == SGPMP_F32)
+        return launch_update<float>(*shape, temperature, step_size, costs, samples, means, grad, weights, (cudaStream_t)stream);
+    return launch_update<double>(*shape, temperature, step_size, costs, samples, means, grad, weights, (cudaStream_t)stream);
+}
+
+extern "C" int sgpmp_local_stats(const sgpmp_shape_t* shape, double temperature, const void* costs, const void* eps,
+                                 void* stats, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_local_stats: invalid shape");
+    SGPMP_REQUIRE(costs && eps && stats, "sgpmp_local_stats: null pointer");
+    SGPMP_REQUIRE(temperature > 0, "sgpmp_local_stats: temperature must be > 0");
+    if (shape->dtype == SGPMP_F32)
+        return launch_local_stats<float>(*shape, temperature, costs, eps, stats, (cudaStream_t)stream);
+    return launch_local_stats<double>(*shape, temperature, costs, eps, stats, (cudaStream_t)stream);
+}
+
+extern "C" int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size, const void* stats,
+                                 void* means, void* grad, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_apply_stats: invalid shape");
+    SGPMP_REQUIRE(tables && stats && means, "sgpmp_apply_stats: null pointer");
+    if (shape->dtype == SGPMP_F32)
+        return launch_apply_stats<float>(*shape, tables, step_size, stats, means, grad, (cudaStream_t)stream);
+    return launch_apply_stats<double>(*shape, tables, step_size, stats, means, grad, (cudaStream_t)stream);
+}

@@ -1,0 +1,205 @@
+"""Tensor-level wrappers over the C-ABI (include/stoch_gpmp_b200.h).
+
+torch is used for device memory and the current stream only; all arithmetic happens in libsgpmp.so.
+Every function raises if handed CPU tensors: there is no CPU path in this package.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.SGPMP_F32, torch.float64: _lib.SGPMP_F64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _req(t, name, dtype=None, shape=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s — stoch_gpmp_b200 runs on CUDA devices only (no CPU fallback)" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t
+
+
+def make_shape(B, G, K, S, T, n_dof, dtype, problem_gid0=0):
+    if dtype not in _DT:
+        raise TypeError("dtype must be torch.float32 or torch.float64, got %s" % dtype)
+    return _lib.Shape(B=B, G=G, K=K, S=S, T=T, n_dof=n_dof, dtype=_DT[dtype], reserved=0, problem_gid0=problem_gid0)
+
+
+def prior_factor(D, O):
+    """K1.  D [n_priors,T,3], O [n_priors,T-1,4] (float64, CUDA) -> (tables [n_priors,T,16], not_pd [n_priors])."""
+    lib = _lib.load()
+    _req(D, "D", torch.float64)
+    _req(O, "O", torch.float64)
+    n, T = D.shape[0], D.shape[1]
+    if tuple(D.shape) != (n, T, 3) or tuple(O.shape) != (n, T - 1, 4):
+        raise ValueError("prior_factor: D must be [n,T,3] and O [n,T-1,4]")
+    tables = torch.empty(n, T, _lib.TABLE_STRIDE, dtype=torch.float64, device=D.device)
+    not_pd = torch.empty(n, dtype=torch.int32, device=D.device)
+    with torch.cuda.device(D.device):
+        _lib.check(lib.sgpmp_prior_factor(n, T, _ptr(D), _ptr(O), _ptr(tables), _ptr(not_pd), _stream()), "sgpmp_prior_factor")
+    return tables, not_pd
+
+
+def prior_dense_L(tables, n_dof, dtype):
+    """Dense scale_tril [M,M] of one prior (tables [T,16])."""
+    lib = _lib.load()
+    _req(tables, "tables", torch.float64)
+    T = tables.shape[0]
+    M = T * 2 * n_dof
+    L = torch.empty(M, M, dtype=dtype, device=tables.device)
+    with torch.cuda.device(tables.device):
+        _lib.check(lib.sgpmp_prior_dense_L(T, n_dof, _ptr(tables), _DT[dtype], _ptr(L), _stream()), "sgpmp_prior_dense_L")
+    return L
+
+
+def sample(shape, tables, means, eps_in=None, seed=0, draw=0, want_eps=False):
+    """K2.  means [B,NP,T,d] -> samples [B,NP,T,d,S] (S-minor).  eps_in, if given, has the samples layout."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt = means.dtype
+    _req(tables, "tables", torch.float64, (T, _lib.TABLE_STRIDE))
+    _req(means, "means", None, (B, NP, T, d))
+    if eps_in is not None:
+        _req(eps_in, "eps_in", dt, (B, NP, T, d, S))
+    out = torch.empty(B, NP, T, d, S, dtype=dt, device=means.device)
+    eps_out = torch.empty_like(out) if want_eps else None
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_sample(C.byref(shape), _ptr(tables), _ptr(means), _ptr(eps_in), seed, draw, _ptr(out),
+                                    _ptr(eps_out), _stream()), "sgpmp_sample")
+    return (out, eps_out) if want_eps else out
+
+
+def cost(shape, desc, tables, samples, means=None, want_terms=False):
+    """K3.  samples [B,NP,T,d,S] -> costs [B,NP,S] (+ terms [5,B,NP,S]).  means=None drops the IS term."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt = samples.dtype
+    _req(samples, "samples", None, (B, NP, T, d, S))
+    if means is not None:
+        _req(tables, "tables", torch.float64, (T, _lib.TABLE_STRIDE))
+        _req(means, "means", dt, (B, NP, T, d))
+    costs = torch.empty(B, NP, S, dtype=dt, device=samples.device)
+    terms = torch.empty(_lib.NUM_TERMS, B, NP, S, dtype=dt, device=samples.device) if want_terms else None
+    with torch.cuda.device(samples.device):
+        _lib.check(lib.sgpmp_cost(C.byref(shape), C.byref(desc), _ptr(tables), _ptr(samples), _ptr(means), _ptr(costs),
+                                  _ptr(terms), _stream()), "sgpmp_cost")
+    return (costs, terms) if want_terms else costs
+
+
+def update(shape, temperature, step_size, costs, samples, means):
+    """K4.  Updates `means` in place; returns (grad [B,NP,T,d], weights [B,NP,S])."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt = means.dtype
+    _req(costs, "costs", dt, (B, NP, S))
+    _req(samples, "samples", dt, (B, NP, T, d, S))
+    _req(means, "means", None, (B, NP, T, d))
+    grad = torch.empty_like(means)
+    weights = torch.empty_like(costs)
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_update(C.byref(shape), float(temperature), float(step_size), _ptr(costs), _ptr(samples),
+                                    _ptr(means), _ptr(grad), _ptr(weights), _stream()), "sgpmp_update")
+    return grad, weights
+
+
+def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0, draw0=0,
+            want_samples=False, want_costs=True, want_weights=True, want_grad=True, want_means_pre=True):
+    """Fused loop.  Updates `means` in place.  Returns dict(means_pre, samples, costs, weights, grad) of the
+    LAST iteration (entries not requested are None)."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt, dev = means.dtype, means.device
+    _req(tables, "tables", torch.float64, (T, _lib.TABLE_STRIDE))
+    _req(means, "means", None, (B, NP, T, d))
+    if eps_in is not None:
+        _req(eps_in, "eps_in", dt, (n_iters, B, NP, T, d, S))
+    out = dict(
+        means_pre=torch.empty_like(means) if want_means_pre else None,
+        samples=torch.empty(B, NP, T, d, S, dtype=dt, device=dev) if want_samples else None,
+        costs=torch.empty(B, NP, S, dtype=dt, device=dev) if want_costs else None,
+        weights=torch.empty(B, NP, S, dtype=dt, device=dev) if want_weights else None,
+        grad=torch.empty_like(means) if want_grad else None,
+    )
+    with torch.cuda.device(dev):
+        _lib.check(lib.sgpmp_iterate(C.byref(shape), C.byref(desc), _ptr(tables), float(step_size), int(n_iters),
+                                     _ptr(eps_in), seed, draw0, _ptr(means), _ptr(out["means_pre"]), _ptr(out["samples"]),
+                                     _ptr(out["costs"]), _ptr(out["weights"]), _ptr(out["grad"]), _stream()),
+                   "sgpmp_iterate")
+    return out
+
+
+def local_stats(shape, temperature, costs, eps):
+    """Split-particle mode: (m, Z, A[M]) per particle of this rank's samples -> stats [B,NP,M+2]."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt = costs.dtype
+    _req(costs, "costs", None, (B, NP, S))
+    _req(eps, "eps", dt, (B, NP, T, d, S))
+    stats = torch.empty(B, NP, T * d + 2, dtype=dt, device=costs.device)
+    with torch.cuda.device(costs.device):
+        _lib.check(lib.sgpmp_local_stats(C.byref(shape), float(temperature), _ptr(costs), _ptr(eps), _ptr(stats), _stream()),
+                   "sgpmp_local_stats")
+    return stats
+
+
+def apply_stats(shape, tables, step_size, stats, means):
+    """mu += step * L (A/Z) in place; returns grad."""
+    lib = _lib.load()
+    B, NP, T, d = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof
+    _req(stats, "stats", means.dtype, (B, NP, T * d + 2))
+    _req(means, "means", None, (B, NP, T, d))
+    grad = torch.empty_like(means)
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_apply_stats(C.byref(shape), _ptr(tables), float(step_size), _ptr(stats), _ptr(means), _ptr(grad),
+                                         _stream()), "sgpmp_apply_stats")
+    return grad
+
+
+def merge_stats(stats_list):
+    """Log-sum-exp merge of per-rank (m, Z, A) statistics (the arithmetic of the split-mode exchange;
+    torch.distributed all_gather supplies `stats_list` across ranks).  Pure tensor glue on any device."""
+    st = torch.stack(list(stats_list), dim=0)              # [R, B, NP, M+2]
+    m = st[..., 0]
+    m_all = m.max(dim=0).values
+    scale = torch.exp(m - m_all.unsqueeze(0))              # [R, B, NP]
+    Z = (st[..., 1] * scale).sum(0)
+    A = (st[..., 2:] * scale.unsqueeze(-1)).sum(0)
+    return torch.cat([m_all.unsqueeze(-1), Z.unsqueeze(-1), A], dim=-1)
+
+
+def fk_link_positions(fk, q):
+    """Link-frame origins [N, L, 3] of configurations q [N, n] for a robots.SerialChainFK (CUDA FK code)."""
+    lib = _lib.load()
+    _req(q, "q")
+    n = fk.n_dofs
+    if q.dim() != 2 or q.shape[1] != n:
+        raise ValueError("q must be [N, %d]" % n)
+    d = _lib.CostDesc()
+    d.n_frames = len(fk.joint)
+    d.include_base = 1 if fk.include_base else 0
+    for f in range(len(fk.joint)):
+        for k in range(9):
+            d.chain_R[f][k] = fk.R[f][k]
+        for k in range(3):
+            d.chain_p[f][k] = fk.xyz[f][k]
+        d.chain_joint[f] = fk.joint[f]
+    pos = torch.empty(q.shape[0], fk.num_links, 3, dtype=q.dtype, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.sgpmp_fk_link_positions(C.byref(d), n, _DT[q.dtype], q.shape[0], _ptr(q), _ptr(pos), _stream()),
+                   "sgpmp_fk_link_positions")
+    return pos
