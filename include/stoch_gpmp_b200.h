@@ -187,6 +187,11 @@ int sgpmp_local_stats(const sgpmp_shape_t* shape, double temperature, const void
 int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size,
                       const void* stats, void* means, void* grad, void* stream);
 
+/* Pipe-peak probes for the roofline denominators MEASURED_PEAKS.json lacks (bench.py times them with
+ * CUDA events).  mode 0: FP32 FMA, blocks x 256 threads x iters x 128 FMA; mode 1: MUFU ex2, blocks x 256
+ * threads x iters x 64 ex2.  scratch: >= 4 bytes of device memory. */
+int sgpmp_probe(int32_t mode, int32_t blocks, int32_t iters, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

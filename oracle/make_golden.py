@@ -189,29 +189,11 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
           f'[{rec["it0_costs"].min():.3e}, {rec["it0_costs"].max():.3e}]')
 
 
-PLANAR_SIGMAS = dict(sigma_start_init=1e-3, sigma_goal_init=1e-3, sigma_gp_init=20.,
-                     sigma_start_sample=1e-3, sigma_goal_sample=1e-3, sigma_gp_sample=3)
-PANDA_SIGMAS = dict(sigma_start_init=0.0001, sigma_goal_init=0.1, sigma_gp_init=0.8,
-                    sigma_start_sample=0.001, sigma_goal_sample=0.07, sigma_gp_sample=0.1)
+from oracle.scenarios import (PANDA_SIGMAS, PANDA_START, PLANAR_GOALS, PLANAR_SIGMAS, panda_goals,  # noqa: E402
+                              panda_spheres)
+
 PLANAR_MAP = dict(map_dim=[20, 20], cell_size=0.1, num_obst=15, rand_limits=[[-7.5, 7.5], [-7.5, 7.5]], seed=0)
 SOFT_MAP = dict(map_dim=[8, 8], cell_size=0.1, num_obst=4, rand_limits=[[-1.5, 1.5], [-1.5, 1.5]], seed=1)
-PLANAR_GOALS = [[9, 6, 0., 0.], [9, -3, 0., 0.], [-3, 9, 0., 0.]]
-PANDA_START = [0.012, -0.57, 0., -2.81, 0., 3.037, 0.741] + [0.] * 7
-
-
-def panda_goals(G, seed):
-    rs = np.random.RandomState(seed)
-    lo = np.array([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973])
-    hi = np.array([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973])
-    q = np.clip(np.array(PANDA_START[:7]) + rs.normal(0, 0.5, (G, 7)), lo, hi)
-    return np.concatenate([q, np.zeros((G, 7))], axis=1).tolist()
-
-
-def panda_spheres(O, seed):
-    rs = np.random.RandomState(seed)
-    c = rs.uniform([0.6, -0.2, 0.6], [1.0, 0.2, 1.0], (O, 3))
-    r = rs.uniform(0.1, 0.2, (O, 1))
-    return np.concatenate([c, r], axis=1).tolist()
 
 
 def main():

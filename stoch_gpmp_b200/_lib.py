@@ -56,6 +56,7 @@ SIGNATURES = {
     "sgpmp_iterate": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_local_stats": (C.c_int, [_SP, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    "sgpmp_probe": (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None

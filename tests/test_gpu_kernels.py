@@ -1,0 +1,481 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (stoch_gpmp_b200.ops -> libsgpmp.so).
+
+Checker = oracle/ (numpy) and the golden vectors produced by the real reference (tests/golden).
+Tolerances: fp64 1e-10 relative (factor-dependent quantities are conditioning-limited on one case, see
+helpers.FACTOR_TOL_F64), fp32 1e-5 relative against the reference run with the same prior factor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox as OPH
+from oracle import planner as OP
+from oracle import prior as P
+from oracle import sampler as SMP
+from oracle import fk as OFK
+
+from helpers import (GOLDEN, GOLDEN_F32, GOLDEN_F64, FACTOR_TOL_F64, TOL_F32, TOL_F64, eps_ref_to_traj, from_sminor,
+                     load, n_iters, rel, to_sminor)
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from stoch_gpmp_b200 import ops
+    return ops
+
+
+def _tables(spec, dev, which='sample'):
+    from stoch_gpmp_b200.planner import prior_blocks
+    goal = spec[f'sigma_goal_{which}'] if spec.get('goals') is not None else None
+    D, O = prior_blocks(spec['T'], spec['dt'], spec[f'sigma_start_{which}'], spec[f'sigma_gp_{which}'], goal)
+    Dt = torch.tensor([D], dtype=torch.float64, device=dev)
+    Ot = torch.tensor([O], dtype=torch.float64, device=dev)
+    tables, bad = _ops().prior_factor(Dt, Ot)
+    assert int(bad[0]) == 0
+    return tables[0].contiguous()
+
+
+def _lowered(spec, dev, dtype, B=1):
+    """Build product cost objects from a spec and lower them."""
+    from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
+    from stoch_gpmp_b200.costs.fields import LinkDistanceField
+    from stoch_gpmp_b200.envs.occupancy import ObstacleMap
+    from stoch_gpmp_b200.robots import PandaFK
+    ta = dict(device=dev, dtype=dtype)
+    n, T = spec['n_dof'], spec['T']
+    cl = [CostGP(n, T, torch.tensor(spec['start'], **ta), spec['dt'],
+                 dict(sigma_start=spec['cost_sigma_start'], sigma_gp=spec['cost_sigma_gp']), ta)]
+    if spec.get('goals') is not None and spec.get('sigma_goal_prior') is not None:
+        cl.append(CostGoalPrior(n, T, multi_goal_states=torch.tensor(spec['goals'], **ta), num_particles_per_goal=spec['K'],
+                                num_samples=spec['S'], sigma_goal_prior=spec['sigma_goal_prior'], tensor_args=ta))
+    FK = None
+    if 'map' in spec:
+        H = spec['map'].shape[0]
+        om = ObstacleMap([2, 2], 1.0, tensor_args=ta)
+        om.map = spec['map'].copy()
+        om.cell_size = spec['map_cell_size']
+        om.origin_xi, om.origin_yi = spec['map_origin']
+        cl.append(CostCollision(n, T, field=om, sigma_coll=spec['sigma_coll']))
+    if 'spheres' in spec:
+        FK = PandaFK()
+        cl.append(CostCollision(n, T, field=LinkDistanceField(tensor_args=ta), sigma_coll=spec['sigma_coll']))
+    comp = CostComposite(n, T, cl, FK=FK, tensor_args=ta)
+    G = spec['G']
+    return comp, comp.lower(B, G, dev, dtype)
+
+
+def _obs(spec, dev, dtype):
+    return {'obstacle_spheres': torch.tensor(spec['spheres'], device=dev, dtype=dtype).unsqueeze(0)} if 'spheres' in spec else {}
+
+
+# --------------------------------------------------------------------------------------------- K1 prior
+@pytest.mark.parametrize("name", GOLDEN)
+def test_prior_tables_match_oracle(name, cuda):
+    spec = OP.spec_from_golden(load(name))
+    tab = _tables(spec, cuda).cpu().numpy()
+    D, O, fac = OP.sampling_prior(spec)
+    G = np.stack([tab[:, 0], tab[:, 1], tab[:, 2]], 1)
+    Go = np.stack([fac['G'][:, 0, 0], fac['G'][:, 1, 0], fac['G'][:, 1, 1]], 1)
+    Ho = fac['H'].reshape(-1, 4)
+    # same operation order, IEEE double, no FMA: expected bit-identical; allow a few ulp
+    assert rel(G, Go) < 1e-14
+    assert rel(tab[:, 3:7], Ho) < 1e-14
+    assert np.array_equal(tab[:, 7:10], np.stack([D[:, 0, 0], D[:, 0, 1], D[:, 1, 1]], 1))
+    assert np.array_equal(tab[:-1, 10:14], O.reshape(-1, 4))
+
+
+@pytest.mark.parametrize("name", GOLDEN_F64)
+def test_prior_dense_L_matches_reference(name, cuda):
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    L = _ops().prior_dense_L(_tables(spec, cuda), spec['n_dof'], torch.float64).cpu().numpy()
+    assert rel(L, g['L']) < FACTOR_TOL_F64.get(name, TOL_F64)
+
+
+@pytest.mark.parametrize("T,n", [(64, 2), (128, 4), (256, 7), (1024, 14)])
+def test_prior_sweep_fp64(T, n, cuda):
+    """C5: prior construction for long horizons; moments against the per-DoF dense covariance
+    (valid because the precision decouples per DoF)."""
+    spec = dict(T=T, dt=0.02, goals=np.zeros((1, 2 * n)), sigma_start_sample=1e-3, sigma_gp_sample=3.0, sigma_goal_sample=1e-3)
+    tab = _tables(spec, cuda)
+    D, O = P.precision_blocks(T, 0.02, 1e-3, 3.0, 1e-3)
+    fac = P.banded_factor(D, O)
+    t = tab.cpu().numpy()
+    assert rel(t[:, [0, 1, 2]], np.stack([fac['G'][:, 0, 0], fac['G'][:, 1, 0], fac['G'][:, 1, 1]], 1)) < 1e-13
+    if T <= 256:
+        L1 = _ops().prior_dense_L(tab, 1, torch.float64).cpu().numpy()        # one DoF: 2T x 2T
+        Sigma = np.linalg.inv(P.dense_from_blocks(D, O, 1))
+        assert rel(L1 @ L1.T, Sigma) < 1e-5
+    if T * n <= 512:
+        Ln = _ops().prior_dense_L(tab, n, torch.float64).cpu().numpy()
+        assert rel(Ln, P.dense_scale_tril(fac['G'], fac['H'], n)) < 1e-12
+
+
+def test_prior_not_pd_flag(cuda):
+    D, O = P.precision_blocks(8, 0.1, 1.0, 1.0, 1.0)
+    D[3] *= -1
+    Dt = torch.tensor(np.stack([D[:, 0, 0], D[:, 0, 1], D[:, 1, 1]], 1)[None], device=cuda)
+    Ot = torch.tensor(O.reshape(1, -1, 4), device=cuda)
+    _, bad = _ops().prior_factor(Dt.contiguous(), Ot.contiguous())
+    assert int(bad[0]) == 1 + 3
+
+
+# -------------------------------------------------------------------------------------------- K2 sample
+@pytest.mark.parametrize("name", GOLDEN)
+def test_sample_injected_eps_matches_reference(name, cuda):
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    T, d = spec['T'], 2 * spec['n_dof']
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(1, spec['G'], spec['K'], spec['S'], T, spec['n_dof'], dt)
+    for it in range(n_iters(g, pre0)):
+        pre = f'{pre0}it{it}_'
+        eps = torch.tensor(to_sminor(eps_ref_to_traj(g[pre + 'eps'], T, d)), device=cuda)
+        mu = torch.tensor(g[pre + 'means_pre'][None], device=cuda)
+        x = from_sminor(_ops().sample(sh, tab, mu, eps_in=eps).cpu().numpy())[0]
+        tol = TOL_F32 if f32 else FACTOR_TOL_F64.get(name, TOL_F64)
+        assert rel(x, g[pre + 'samples']) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("T,n,S", [(16, 2, 40), (7, 3, 33), (64, 7, 64)])
+def test_sample_inkernel_rng_matches_oracle_stream(dtype, T, n, S, cuda):
+    """The kernel's Philox/Box-Muller stream == oracle/philox.py (odd T exercises the half-used last pair)."""
+    B, G, K = 2, 2, 2
+    NP = G * K
+    spec = dict(T=T, dt=0.05, goals=np.zeros((G, 2 * n)), sigma_start_sample=0.05, sigma_gp_sample=0.5, sigma_goal_sample=0.05)
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype, problem_gid0=5)
+    mu = torch.zeros(B, NP, T, 2 * n, dtype=dtype, device=cuda)
+    x, eps = _ops().sample(sh, tab, mu, seed=0x1234567887654321, draw=3, want_eps=True)
+    eps = from_sminor(eps.cpu().numpy())
+    want = OPH.normals(0x1234567887654321, 3, 5 * NP + np.arange(B * NP), S, T, n).reshape(B, NP, S, T, 2 * n)
+    if dtype == torch.float64:
+        assert np.abs(eps - want).max() < 1e-12
+    else:
+        # fp32 rounds (w + 0.5) 2^-32 to 24 bits: |d eps| <~ 3e-6 except in the vanishing-r corner u1 -> 1
+        err = np.abs(eps - want)
+        assert np.quantile(err, 0.999) < 5e-6 and err.max() < 2e-3
+    _, _, fac = OP.sampling_prior(dict(spec, n_dof=n))
+    y = SMP.banded_transform(fac['G'], fac['H'], eps.astype(np.float64))
+    assert rel(from_sminor(x.cpu().numpy()), y) < (1e-12 if dtype == torch.float64 else 2e-6)
+
+
+def test_sample_moments_vs_dense_covariance(cuda):
+    """Sample covariance of many in-kernel draws against the dense reference covariance P^-1."""
+    T, n, S = 6, 1, 200000
+    spec = dict(T=T, dt=0.1, goals=np.zeros((1, 2)), sigma_start_sample=0.3, sigma_gp_sample=1.0, sigma_goal_sample=0.3, n_dof=n)
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(1, 1, 1, S, T, n, torch.float64)
+    mu = torch.zeros(1, 1, T, 2, dtype=torch.float64, device=cuda)
+    x = from_sminor(_ops().sample(sh, tab, mu, seed=7, draw=0).cpu().numpy())[0, 0].reshape(S, -1)
+    D, O, _ = OP.sampling_prior(spec)
+    Sigma = np.linalg.inv(P.dense_from_blocks(D, O, n))
+    C = np.cov(x.T)
+    assert np.abs(x.mean(0)).max() < 4 * np.sqrt(np.diag(Sigma).max() / S)
+    assert rel(C, Sigma) < 0.02
+
+
+def test_sample_linearity_full_size(cuda):
+    """Size-independent property at the C4 per-particle shape: y(2 eps) = 2 y(eps), y(0) = 0."""
+    T, n, S = 64, 7, 512
+    spec = dict(T=T, dt=0.05, goals=np.zeros((4, 14)), sigma_start_sample=0.001, sigma_gp_sample=0.1, sigma_goal_sample=0.07)
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(2, 4, 1, S, T, n, torch.float32)
+    mu = torch.randn(2, 4, T, 14, device=cuda)
+    x1, eps = _ops().sample(sh, tab, mu, seed=1, draw=0, want_eps=True)
+    x2 = _ops().sample(sh, tab, mu, eps_in=(2 * eps).contiguous())
+    y1 = x1 - mu.unsqueeze(-1)
+    y2 = x2 - mu.unsqueeze(-1)
+    assert float((y2 - 2 * y1).abs().max() / y1.abs().max()) < 1e-5
+    x0 = _ops().sample(sh, tab, mu, eps_in=torch.zeros_like(eps))
+    assert torch.equal(x0, mu.unsqueeze(-1).expand_as(x0))
+
+
+# ---------------------------------------------------------------------------------------------- K3 cost
+@pytest.mark.parametrize("name", GOLDEN)
+def test_cost_terms_match_reference(name, cuda):
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    tol = TOL_F32 if f32 else FACTOR_TOL_F64.get(name, TOL_F64)
+    T = spec['T']
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dt)
+    sh = _ops().make_shape(1, spec['G'], spec['K'], spec['S'], T, spec['n_dof'], dt)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dt).unsqueeze(0) if 'spheres' in spec else None
+    D, O, _ = OP.sampling_prior(spec)
+    for it in range(n_iters(g, pre0)):
+        pre = f'{pre0}it{it}_'
+        xs = torch.tensor(to_sminor(g[pre + 'samples']), device=cuda)
+        mu = torch.tensor(g[pre + 'means_pre'][None], device=cuda)
+        costs, terms = _ops().cost(sh, low.desc(spec['temperature'], sp), tab, xs, mu, want_terms=True)
+        terms = terms.cpu().numpy()[:, 0]
+        costs = costs.cpu().numpy()[0]
+        assert rel(terms[0], g[pre + 'term_start']) < tol
+        assert rel(terms[0] + terms[1], g[pre + 'term_gp']) < tol
+        if 'goals' in g.files and spec['sigma_goal_prior']:
+            assert rel(terms[2], g[pre + 'term_goal']) < tol
+        if spec['sigma_coll']:
+            if 'map' in spec:
+                # integer index work: the occupancy sums must be bit-exact
+                assert np.array_equal(terms[3], g[pre + 'term_coll'])
+            else:
+                assert rel(terms[3], g[pre + 'term_coll']) < (3e-5 if f32 else 10 * tol)
+        # IS term: against the fp64 oracle everywhere; against the reference where the reference itself is
+        # accurate (fp64).  The fp32 reference's IS term carries up to 4e-3 of cancellation noise.
+        _, tot_o = OP.eval_costs(spec, g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O)
+        is_o = OP.C.cost_importance(g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O, spec['temperature'])
+        assert rel(terms[4], is_o) < (TOL_F32 if f32 else 1e-10)
+        assert rel(costs, tot_o) < (TOL_F32 if f32 else 1e-10)
+        if not f32:
+            assert rel(terms[4], g[pre + 'term_is']) < 1e-9
+            assert rel(costs, g[pre + 'costs']) < 1e-10
+        else:
+            assert rel(costs, g[pre + 'costs']) < 1e-2      # bounded by the fp32 reference's own IS-term noise
+
+
+def test_cost_eval_dropin(cuda):
+    """CostComposite.eval(trajs) on CUDA tensors == sum of the reference's cost terms (no IS term)."""
+    g = load('planar_f64')
+    spec = OP.spec_from_golden(g)
+    comp, _ = _lowered(spec, cuda, torch.float64)
+    x = torch.tensor(g['it0_samples'], device=cuda)
+    got = comp.eval(x).cpu().numpy().reshape(g['it0_costs'].shape)
+    want = g['it0_term_gp'] + g['it0_term_goal'] + g['it0_term_coll']
+    assert rel(got, want) < 1e-12
+    # single cost objects
+    assert rel(comp.cost_list[0].eval(x.reshape(-1, spec['T'], 4)).cpu().numpy().reshape(want.shape), g['it0_term_gp']) < 1e-12
+
+
+def test_map_lookup_edges(cuda):
+    """Out-of-range points clamp to the border, value = map[iy][ix] (obst_map.py:173-181); fp32 and fp64."""
+    from stoch_gpmp_b200.envs.occupancy import ObstacleMap
+    from oracle import costs as C
+    rs = np.random.RandomState(0)
+    for dtype, npdt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        om = ObstacleMap([4, 4], 0.1, tensor_args=dict(device=cuda, dtype=dtype))
+        om.map = rs.randint(0, 3, om.map.shape).astype(np.float64)
+        xy = np.concatenate([rs.uniform(-3, 3, (4000, 2)), np.array([[-2.0, -2.0], [2.0, 2.0], [1.95, -1.95], [0.0, 0.0], [0.1, 0.2], [-0.1, 0.3]])]).astype(npdt)
+        got = om.compute_cost(torch.tensor(xy, device=cuda)).cpu().numpy()
+        want = C.map_lookup(xy, om.map.astype(npdt), 0.1, om.origin_xi, om.origin_yi)
+        assert np.array_equal(got, want)
+
+
+def test_fk_known_answers_cuda(cuda):
+    from stoch_gpmp_b200.robots import PandaFK
+    fk = PandaFK()
+    q = torch.tensor([[0.] * 7, [0.012, -0.57, 0., -2.81, 0., 3.037, 0.741]], dtype=torch.float64, device=cuda)
+    pos = _ops().fk_link_positions(fk, q).cpu().numpy()
+    assert pos.shape == (2, 11, 3)
+    assert np.allclose(pos[0, 8], [0.088, 0.0, 0.926], atol=1e-9)
+    assert np.allclose(pos[0, 10], [0.088, 0.0, 0.826], atol=1e-9)
+    assert np.allclose(pos[1, 10], [0.460816, 0.005530, 0.388328], atol=2e-6)
+    rs = np.random.RandomState(1)
+    qr = rs.uniform(-2.8, 2.8, (257, 7))
+    want = OFK.fk_all_links(qr)[:, :, :3, 3]
+    assert rel(_ops().fk_link_positions(fk, torch.tensor(qr, device=cuda)).cpu().numpy(), want) < 1e-13
+    assert rel(_ops().fk_link_positions(fk, torch.tensor(qr, device=cuda, dtype=torch.float32)).cpu().numpy(), want) < 2e-6
+
+
+# -------------------------------------------------------------------------------------------- K4 update
+@pytest.mark.parametrize("name", GOLDEN)
+def test_update_matches_reference(name, cuda):
+    """Feed the REFERENCE's costs and samples: weights, grad and new means must match."""
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    sh = _ops().make_shape(1, spec['G'], spec['K'], spec['S'], spec['T'], spec['n_dof'], dt)
+    for it in range(n_iters(g, pre0)):
+        pre = f'{pre0}it{it}_'
+        xs = torch.tensor(to_sminor(g[pre + 'samples']), device=cuda)
+        mu = torch.tensor(g[pre + 'means_pre'][None], device=cuda).clone()
+        c = torch.tensor(g[pre + 'costs'][None], device=cuda)
+        grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], c, xs, mu)
+        assert np.abs(w.cpu().numpy()[0] - g[pre + 'weights']).max() < (1e-5 if f32 else 1e-12)
+        assert rel(grad.cpu().numpy()[0], g[pre + 'grad']) < (TOL_F32 if f32 else 1e-10)
+        assert rel(mu.cpu().numpy()[0], g[pre + 'means_post']) < (1e-6 if f32 else 1e-12)
+
+
+# ------------------------------------------------------------------------------------------ fused loop
+@pytest.mark.parametrize("name", GOLDEN)
+def test_fused_iteration_matches_reference(name, cuda):
+    """sgpmp_iterate with the reference's eps: samples, costs, weights, grad, means — chained iterations."""
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    ftol = TOL_F32 if f32 else FACTOR_TOL_F64.get(name, TOL_F64)
+    T, d = spec['T'], 2 * spec['n_dof']
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dt)
+    sh = _ops().make_shape(1, spec['G'], spec['K'], spec['S'], T, spec['n_dof'], dt)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dt).unsqueeze(0) if 'spheres' in spec else None
+    D, O, _ = OP.sampling_prior(spec)
+    for it in range(n_iters(g, pre0)):
+        pre = f'{pre0}it{it}_'
+        eps = torch.tensor(to_sminor(eps_ref_to_traj(g[pre + 'eps'], T, d)), device=cuda).unsqueeze(0).contiguous()
+        mu = torch.tensor(g[pre + 'means_pre'][None], device=cuda).clone()
+        out = _ops().iterate(sh, low.desc(spec['temperature'], sp), tab, spec['step_size'], 1, mu, eps_in=eps, want_samples=True)
+        assert np.array_equal(out['means_pre'].cpu().numpy()[0], g[pre + 'means_pre'])
+        assert rel(from_sminor(out['samples'].cpu().numpy())[0], g[pre + 'samples']) < ftol
+        costs = out['costs'].cpu().numpy()[0]
+        if not f32:
+            assert rel(costs, g[pre + 'costs']) < 1e-10
+            assert np.abs(out['weights'].cpu().numpy()[0] - g[pre + 'weights']).max() < 1e-7
+            assert rel(out['grad'].cpu().numpy()[0], g[pre + 'grad']) < max(10 * ftol, 1e-9)
+            assert rel(mu.cpu().numpy()[0], g[pre + 'means_post']) < ftol
+        else:
+            # fp32: total costs vs the accurate (fp64) oracle; weights/update from the kernel's own costs
+            r = OP.iterate(spec, g[pre + 'means_pre'], eps_ref_to_traj(g[pre + 'eps'], T, d))
+            assert rel(costs, r['costs']) < TOL_F32
+            from oracle import update as U
+            mp, grad, w = U.update(g[pre + 'means_pre'].astype(np.float64), r['samples'], costs.astype(np.float64),
+                                   spec['temperature'], spec['step_size'])
+            assert np.abs(out['weights'].cpu().numpy()[0] - w).max() < 1e-5
+            assert rel(out['grad'].cpu().numpy()[0], grad) < 2e-5
+            assert rel(mu.cpu().numpy()[0], mp) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("case", ["planar", "panda"])
+def test_fused_equals_separate_kernels_inkernel_rng(case, dtype, cuda):
+    """Fused loop (in-kernel Philox, 3 iterations in one launch) == K2 -> K3 -> K4 chained with the same
+    draw indices.  Soft sigmas so that many samples carry weight (exercises the weighted eps-sum pass)."""
+    g = load('planar_soft_f64' if case == 'planar' else 'panda_soft_f64')
+    spec = OP.spec_from_golden(g)
+    B, S = 3, 96 if case == 'planar' else 40
+    spec = dict(spec, S=S)
+    T, n, G, K = spec['T'], spec['n_dof'], spec['G'], spec['K']
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dtype, B=B)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dtype).unsqueeze(0) if 'spheres' in spec else None
+    desc = low.desc(spec['temperature'], sp)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype, problem_gid0=11)
+    mu0 = torch.tensor(g['it0_means_pre'], device=cuda, dtype=dtype).unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
+    mu0 += 0.01 * torch.arange(B, device=cuda, dtype=dtype).view(B, 1, 1, 1)
+    mu_f = mu0.clone()
+    out = _ops().iterate(sh, desc, tab, spec['step_size'], 3, mu_f, seed=99, draw0=4, want_samples=True)
+    mu_s = mu0.clone()
+    for it in range(3):
+        pre_means = mu_s.clone()
+        xs = _ops().sample(sh, tab, mu_s, seed=99, draw=4 + it)
+        c = _ops().cost(sh, desc, tab, xs, mu_s)
+        grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], c, xs, mu_s)
+    tol = 2e-4 if dtype == torch.float32 else 1e-9
+    assert float((out['means_pre'] - pre_means).abs().max() / pre_means.abs().max()) < tol
+    assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < tol
+    assert float((out['costs'] - c).abs().max() / c.abs().max()) < tol
+    assert float((out['weights'] - w).abs().max()) < (5e-3 if dtype == torch.float32 else 1e-8)
+    assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < (5e-3 if dtype == torch.float32 else 1e-8)
+    assert float((mu_f - mu_s).abs().max() / mu_s.abs().max()) < tol
+    ess = 1.0 / (w.double() ** 2).sum(-1)
+    assert float(ess.max()) > 1.5          # the weighted pass really was exercised
+
+
+def test_fused_problem_sharding_invariance(cuda):
+    """B problems in one launch == the same problems launched as two shards with problem_gid0 offsets."""
+    g = load('panda_soft_f32')
+    spec = dict(OP.spec_from_golden(g), S=64)
+    T, n, G, K, S = spec['T'], spec['n_dof'], spec['G'], spec['K'], spec['S']
+    B = 4
+    dtype = torch.float32
+    tab = _tables(spec, cuda)
+    rs = np.random.RandomState(3)
+    starts = torch.tensor(spec['start'][None] + 0.05 * rs.randn(B, 2 * n), device=cuda, dtype=dtype)
+    goals = torch.tensor(spec['goals'][None] + 0.05 * rs.randn(B, G, 2 * n), device=cuda, dtype=dtype)
+    spheres = torch.tensor(spec['spheres'][None] + 0.02 * rs.randn(B, len(spec['spheres']), 4), device=cuda, dtype=dtype)
+    mu0 = torch.tensor(g['it0_means_pre'], device=cuda, dtype=dtype).unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
+
+    def run(lo, hi):
+        from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
+        from stoch_gpmp_b200.costs.fields import LinkDistanceField
+        from stoch_gpmp_b200.robots import PandaFK
+        ta = dict(device=cuda, dtype=dtype)
+        comp = CostComposite(n, T, [
+            CostGP(n, T, starts[lo:hi], spec['dt'], dict(sigma_start=spec['cost_sigma_start'], sigma_gp=spec['cost_sigma_gp']), ta),
+            CostGoalPrior(n, T, multi_goal_states=goals[lo:hi], num_particles_per_goal=K, num_samples=S,
+                          sigma_goal_prior=spec['sigma_goal_prior'], tensor_args=ta),
+            CostCollision(n, T, field=LinkDistanceField(tensor_args=ta), sigma_coll=spec['sigma_coll'])], FK=PandaFK(), tensor_args=ta)
+        low = comp.lower(hi - lo, G, cuda, dtype)
+        sh = _ops().make_shape(hi - lo, G, K, S, T, n, dtype, problem_gid0=lo)
+        mu = mu0[lo:hi].clone()
+        out = _ops().iterate(sh, low.desc(spec['temperature'], spheres[lo:hi].contiguous()), tab, spec['step_size'], 2, mu, seed=5, draw0=0)
+        return mu, out['costs']
+    mu_all, c_all = run(0, B)
+    mu_a, c_a = run(0, 1)
+    mu_b, c_b = run(1, B)
+    assert torch.equal(mu_all, torch.cat([mu_a, mu_b]))
+    assert torch.equal(c_all, torch.cat([c_a, c_b]))
+
+
+def test_fused_full_size_properties(cuda):
+    """C4 per-problem shape (G=4, K=1, S=512, T=64, n=7, fp32) on a few problems: size-independent
+    properties — weights sum to one, grad == sum_s w_s (x_s - mu) on the emitted samples (K4 on the fused
+    kernel's own outputs), determinism, and emitted costs == K3 on the emitted samples."""
+    T, n, G, K, S, B = 64, 7, 4, 1, 512, 3
+    dtype = torch.float32
+    rs = np.random.RandomState(0)
+    from oracle.scenarios import PANDA_START, panda_goals, panda_spheres
+    spec = dict(n_dof=n, T=T, dt=0.05, G=G, K=K, S=S, temperature=1.0, step_size=0.1, start=np.array(PANDA_START),
+                goals=np.array(panda_goals(G, 3)), cost_sigma_start=1e-4, cost_sigma_gp=7e-4, sigma_goal_prior=20., sigma_coll=0.01,
+                spheres=np.array(panda_spheres(5, 3)), sigma_start_sample=1e-3, sigma_gp_sample=0.1, sigma_goal_sample=0.07)
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dtype, B=B)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dtype).unsqueeze(0)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype)
+    from stoch_gpmp_b200.planner import StochGPMPBatch  # noqa: F401  (import check)
+    mu0 = torch.tensor(P.const_vel_trajectories(spec['start'], spec['goals'], 0.05, T, n, K).reshape(1, G * K, T, 2 * n),
+                       device=cuda, dtype=dtype).repeat(B, 1, 1, 1).contiguous()
+    res = []
+    for rep in range(2):
+        mu = mu0.clone()
+        out = _ops().iterate(sh, low.desc(1.0, sp), tab, 0.1, 1, mu, seed=1, draw0=0, want_samples=True)
+        res.append((mu, out))
+    (mu1, o1), (mu2, o2) = res
+    for k in ('samples', 'costs', 'weights', 'grad'):
+        assert torch.equal(o1[k], o2[k])
+    assert torch.equal(mu1, mu2)
+    assert float((o1['weights'].sum(-1) - 1).abs().max()) < 1e-5
+    c3 = _ops().cost(sh, low.desc(1.0, sp), tab, o1['samples'], mu0)
+    assert float((c3 - o1['costs']).abs().max() / c3.abs().max()) < 1e-6
+    mu_k4 = mu0.clone()
+    grad, w = _ops().update(sh, 1.0, 0.1, o1['costs'], o1['samples'], mu_k4)
+    assert float((w - o1['weights']).abs().max()) < 1e-6
+    assert float((grad - o1['grad']).abs().max() / grad.abs().max()) < 1e-4
+    assert float((mu_k4 - mu1).abs().max() / mu1.abs().max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- split mode
+def test_split_particle_stats_equal_single_update(cuda):
+    """One problem's samples split in two halves: local stats -> log-sum-exp merge -> apply == K4 on all."""
+    g = load('planar_soft_f64')
+    spec = OP.spec_from_golden(g)
+    T, n, G, K, S = spec['T'], spec['n_dof'], spec['G'], spec['K'], spec['S']
+    dt = torch.float64
+    tab = _tables(spec, cuda)
+    eps = torch.tensor(to_sminor(eps_ref_to_traj(g['it0_eps'], T, 2 * n)), device=cuda)
+    xs = torch.tensor(to_sminor(g['it0_samples']), device=cuda)
+    c = torch.tensor(g['it0_costs'][None], device=cuda)
+    mu = torch.tensor(g['it0_means_pre'][None], device=cuda)
+    sh = _ops().make_shape(1, G, K, S, T, n, dt)
+    mu_ref = mu.clone()
+    grad_ref, _ = _ops().update(sh, spec['temperature'], spec['step_size'], c, xs, mu_ref)
+    h = S // 2
+    shh = _ops().make_shape(1, G, K, h, T, n, dt)
+    st = [_ops().local_stats(shh, spec['temperature'], c[..., a:a + h].contiguous(), eps[..., a:a + h].contiguous()) for a in (0, h)]
+    merged = _ops().merge_stats(st).contiguous()
+    mu_split = mu.clone()
+    grad = _ops().apply_stats(sh, tab, spec['step_size'], merged, mu_split)
+    assert rel(grad.cpu().numpy(), grad_ref.cpu().numpy()) < 1e-9
+    assert rel(mu_split.cpu().numpy(), mu_ref.cpu().numpy()) < 1e-12
+    assert rel(mu_split.cpu().numpy()[0], g['it0_means_post']) < 1e-10

@@ -1,0 +1,202 @@
+"""GPU: the Python drop-in (StochGPMP / StochGPMPBatch) end to end against the reference's golden runs.
+
+These tests read like the reference's example scripts: build cost objects, build the planner, call
+optimize() / get_recent_samples().  eps is injected (the reference's torch-drawn normals) through the
+private `_eps` / `_init_eps` hooks.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import planner as OP
+
+from helpers import (GOLDEN, FACTOR_TOL_F64, TOL_F32, TOL_F64, eps_ref_to_traj, load, n_iters, rel, to_sminor)
+from test_gpu_kernels import _lowered, _obs
+
+pytestmark = pytest.mark.gpu
+
+
+def _planner(g, spec, dev, dtype, **over):
+    from stoch_gpmp_b200.planner import StochGPMP
+    comp, _ = _lowered(spec, dev, dtype)
+    ta = dict(device=dev, dtype=dtype)
+    mode = str(g['initial_particle_means_mode']) if 'initial_particle_means_mode' in g.files else None
+    kw = dict(num_particles_per_goal=spec['K'], num_samples=spec['S'], traj_len=spec['T'], opt_iters=1, dt=spec['dt'],
+              n_dof=spec['n_dof'], step_size=spec['step_size'], temperature=spec['temperature'],
+              start_state=torch.tensor(spec['start'], **ta),
+              multi_goal_states=None if spec.get('goals') is None else torch.tensor(spec['goals'], **ta),
+              initial_particle_means=mode, cost=comp, seed=int(g['seed']), tensor_args=ta,
+              **{k: spec[k] for k in ('sigma_start_init', 'sigma_gp_init', 'sigma_goal_init', 'sigma_start_sample',
+                                      'sigma_gp_sample', 'sigma_goal_sample')})
+    kw.update(over)
+    return StochGPMP(**kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_planner_matches_reference_run(name, cuda):
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dtype = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    ftol = TOL_F32 if f32 else FACTOR_TOL_F64.get(name, TOL_F64)
+    T, n = spec['T'], spec['n_dof']
+    d = 2 * n
+    pl = _planner(g, spec, cuda, dtype)
+    assert pl.num_particles == spec['G'] * spec['K']
+    # reset(): initial means from the INIT prior with the reference's init draw
+    if pre0 + 'init_eps' in g.files:
+        pl.reset(_init_eps=torch.tensor(g[pre0 + 'init_eps'], device=cuda))
+    assert tuple(pl.particle_means.shape) == (pl.num_particles, T, d)
+    assert rel(pl.particle_means.cpu().numpy(), g[pre0 + 'means_reset']) < max(ftol, 1e-10)
+    assert rel(pl.Sigma_inv.cpu().numpy(), g['Sigma_inv']) < (1e-6 if f32 else 1e-15)
+    obs = _obs(spec, cuda, dtype)
+    for it in range(n_iters(g, pre0)):
+        pre = f'{pre0}it{it}_'
+        # continue from the reference's own pre-iteration means so that each iteration is checked alone
+        pl.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+        eps = torch.tensor(to_sminor(eps_ref_to_traj(g[pre + 'eps'], T, d)), device=cuda)   # [1,NP,T,d,S] == [n_iters, NP, ...]
+        pos_m, vel_m, pos_s, vel_s, costs, grad = pl.optimize(_eps=eps, **obs)
+        assert tuple(pos_s.shape) == (pl.num_particles, spec['S'], T, n) and tuple(costs.shape) == (pl.num_particles, spec['S'])
+        # optimize() returns the means from BEFORE the update (planner.py:252-253)
+        assert np.array_equal(pos_m.cpu().numpy(), g[pre + 'means_pre'][..., :n])
+        assert np.array_equal(vel_m.cpu().numpy(), g[pre + 'means_pre'][..., n:])
+        assert rel(pos_s.cpu().numpy(), g[pre + 'samples'][..., :n]) < ftol
+        assert rel(vel_s.cpu().numpy(), g[pre + 'samples'][..., n:]) < ftol
+        if not f32:
+            assert rel(costs.cpu().numpy(), g[pre + 'costs']) < 1e-10
+            assert np.abs(pl._weights.cpu().numpy().reshape(g[pre + 'weights'].shape) - g[pre + 'weights']).max() < 1e-7
+            assert rel(grad.cpu().numpy(), g[pre + 'grad']) < max(10 * ftol, 1e-9)
+            assert rel(pl.particle_means.cpu().numpy(), g[pre + 'means_post']) < ftol
+        tr, ct = pl.get_recent_samples()
+        assert torch.equal(tr, pos_s) and torch.equal(ct, vel_s) and tr.data_ptr() != pos_s.data_ptr()
+
+
+def test_final_plans_agree_in_cost_and_collision_freeness(cuda):
+    """north_star: 'final plans must agree in cost and collision-freeness'.  Chain the golden iterations
+    WITHOUT resetting the means in between; compare the final means, their cost and their occupancy."""
+    g = load('planar_f64')
+    spec = OP.spec_from_golden(g)
+    T, n = spec['T'], spec['n_dof']
+    pl = _planner(g, spec, cuda, torch.float64)
+    pl.reset(_init_eps=torch.tensor(g['init_eps'], device=cuda))
+    for it in range(n_iters(g)):
+        eps = torch.tensor(to_sminor(eps_ref_to_traj(g[f'it{it}_eps'], T, 2 * n)), device=cuda)
+        pl.optimize(_eps=eps)
+    final = pl.particle_means.cpu().numpy()
+    want = g[f'it{n_iters(g) - 1}_means_post']
+    assert rel(final, want) < 1e-10
+    from oracle import costs as C
+    occ_got = C.map_lookup(final[:, 1:, :2], spec['map'], spec['map_cell_size'], *spec['map_origin'])
+    occ_want = C.map_lookup(want[:, 1:, :2], spec['map'], spec['map_cell_size'], *spec['map_origin'])
+    assert np.array_equal(occ_got, occ_want)
+
+
+def test_lazy_samples_regenerate_identically(cuda):
+    """return_samples=False writes nothing; get_recent_samples() rebuilds the same samples from the
+    counter-based RNG; state_samples after reset is reproducible too."""
+    g = load('panda_soft_f32')
+    spec = OP.spec_from_golden(g)
+    obs = _obs(spec, cuda, torch.float32)
+    a = _planner(g, spec, cuda, torch.float32)
+    b = _planner(g, spec, cuda, torch.float32)
+    assert torch.equal(a.state_samples, b.state_samples)
+    oa = a.optimize(opt_iters=3, return_samples=True, **obs)
+    ob = b.optimize(opt_iters=3, return_samples=False, **obs)
+    assert ob[2] is None and ob[3] is None
+    assert torch.equal(oa[4], ob[4]) and torch.equal(oa[5], ob[5])
+    ta, tb = a.get_recent_samples(), b.get_recent_samples()
+    assert float((ta[0] - tb[0]).abs().max()) < 1e-6 and float((ta[1] - tb[1]).abs().max()) < 1e-5
+    # three fused iterations == three single-iteration calls
+    c = _planner(g, spec, cuda, torch.float32)
+    for _ in range(3):
+        oc = c.optimize(opt_iters=1, **obs)
+    assert torch.equal(oc[4], oa[4]) and torch.equal(c.particle_means, a.particle_means)
+
+
+def test_reference_method_path_equals_fused(cuda):
+    """sample_and_eval() + _update_distribution() (K2/K3/K4) == optimize() (fused) for the same draw."""
+    g = load('planar_soft_f64')
+    spec = OP.spec_from_golden(g)
+    a = _planner(g, spec, cuda, torch.float64)
+    b = _planner(g, spec, cuda, torch.float64)
+    vel_s, pos_s, vel_m, pos_m, costs = a.sample_and_eval()
+    grad = a._update_distribution(costs, a.state_samples)
+    out = b.optimize()
+    assert rel(costs.cpu().numpy(), out[4].cpu().numpy()) < 1e-12
+    assert rel(pos_s.cpu().numpy(), out[2].cpu().numpy()) < 1e-13
+    assert rel(grad.cpu().numpy(), out[5].cpu().numpy()) < 1e-9
+    assert rel(a.particle_means.cpu().numpy(), b.particle_means.cpu().numpy()) < 1e-12
+    p, v = a.sample_trajectories(7)
+    assert tuple(p.shape) == (a.num_particles, 7, spec['T'], spec['n_dof'])
+
+
+def test_batch_equals_loop_of_singles(cuda):
+    """StochGPMPBatch over B problems == B StochGPMP planners with problem_offset = b (new B axis)."""
+    from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
+    from stoch_gpmp_b200.envs.occupancy import generate_obstacle_map
+    from stoch_gpmp_b200.planner import StochGPMP, StochGPMPBatch
+    from oracle.scenarios import PLANAR_COST, PLANAR_SIGMAS, planar_batch
+    import random
+    B, G, K, S, T, n = 3, 4, 2, 32, 32, 2
+    dtype = torch.float32
+    ta = dict(device=cuda, dtype=dtype)
+    start, goals = planar_batch(B, G, seed0=1)
+    maps = []
+    for b in range(B):
+        random.seed(100 + b)
+        np.random.seed(100 + b)
+        maps.append(generate_obstacle_map(map_dim=[20, 20], cell_size=0.1, random_gen=True, num_obst=10,
+                                          rand_limits=[[-7.5, 7.5], [-7.5, 7.5]], rand_rect_shape=[2, 2], tensor_args=ta)[0])
+
+    def build(cls, sl, field, **kw):
+        s = torch.tensor(start[sl], **ta)
+        gl = torch.tensor(goals[sl], **ta)
+        comp = CostComposite(n, T, [
+            CostGP(n, T, s, 0.02, dict(sigma_start=PLANAR_COST['sigma_start'], sigma_gp=PLANAR_COST['sigma_gp']), ta),
+            CostGoalPrior(n, T, multi_goal_states=gl, num_particles_per_goal=K, num_samples=S,
+                          sigma_goal_prior=PLANAR_COST['sigma_goal_prior'], tensor_args=ta),
+            CostCollision(n, T, field=field, sigma_coll=PLANAR_COST['sigma_coll'])])
+        return cls(num_particles_per_goal=K, num_samples=S, traj_len=T, opt_iters=2, dt=0.02, n_dof=n, step_size=0.5,
+                   temperature=1., start_state=s, multi_goal_states=gl, cost=comp, seed=3, tensor_args=ta, **PLANAR_SIGMAS, **kw)
+    pb = build(StochGPMPBatch, slice(0, B), maps)
+    ob = pb.optimize()
+    for b in range(B):
+        ps = build(StochGPMP, b, maps[b], problem_offset=b)
+        os_ = ps.optimize()
+        assert torch.equal(ps.particle_means, pb.particle_means[b])
+        assert torch.equal(os_[4], ob[4][b]) and torch.equal(os_[5], ob[5][b])
+
+
+def test_error_behaviour(cuda, lib):
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, Cost
+    from stoch_gpmp_b200.planner import StochGPMP
+    g = load('planar_f64')
+    spec = OP.spec_from_golden(g)
+    # CPU device: no fallback
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _planner(g, spec, torch.device('cpu'), torch.float64)
+    # goals must be 2-D (planner.py:60)
+    with pytest.raises(AssertionError):
+        _planner(g, spec, cuda, torch.float64, multi_goal_states=torch.zeros(4, device=cuda, dtype=torch.float64))
+    # non-PD prior -> ValueError (the reference's failure class, mp_priors_multi.py:106)
+    with pytest.raises(ValueError, match="positive definite"):
+        _planner(g, spec, cuda, torch.float64, sigma_gp_sample=float('nan'))
+    # un-lowerable cost object -> NotImplementedError
+
+    class Custom(Cost):
+        pass
+    ta = dict(device=cuda, dtype=torch.float64)
+    comp = CostComposite(2, spec['T'], [CostGP(2, spec['T'], torch.zeros(4, **ta), 0.02, dict(sigma_start=1., sigma_gp=1.), ta),
+                                        Custom(2, spec['T'])])
+    with pytest.raises(NotImplementedError):
+        _planner(g, spec, cuda, torch.float64, cost=comp)
+    # CostGoalPrior built for another (K, S): the reference fails in its reshape (cost_functions.py:379)
+    pl = _planner(g, spec, cuda, torch.float64, num_samples=spec['S'] + 1)
+    with pytest.raises(RuntimeError):
+        pl.optimize()
+    # n_dof without an instantiation
+    with pytest.raises(NotImplementedError):
+        StochGPMP(1, 4, 8, 1, dt=0.1, n_dof=5, start_state=torch.zeros(10, **ta), multi_goal_states=torch.zeros(1, 10, **ta),
+                  cost=None, sigma_start_init=1., sigma_start_sample=1., sigma_goal_init=1., sigma_goal_sample=1.,
+                  sigma_gp_init=1., sigma_gp_sample=1., tensor_args=ta)
