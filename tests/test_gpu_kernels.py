@@ -363,21 +363,29 @@ def test_fused_equals_separate_kernels_inkernel_rng(case, dtype, cuda):
     sh = _ops().make_shape(B, G, K, S, T, n, dtype, problem_gid0=11)
     mu0 = torch.tensor(g['it0_means_pre'], device=cuda, dtype=dtype).unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
     mu0 += 0.01 * torch.arange(B, device=cuda, dtype=dtype).view(B, 1, 1, 1)
-    mu_f = mu0.clone()
-    out = _ops().iterate(sh, desc, tab, spec['step_size'], 3, mu_f, seed=99, draw0=4, want_samples=True)
+    # The loop is chaotic in fp32 (a mean perturbation d changes the logits by ~|dc/dmu| d / tau ~ 200 d here), so
+    # the two paths are compared iteration by iteration from the SAME means; fp64 also checks the 3-iteration chain.
+    tol = 2e-5 if dtype == torch.float32 else 1e-9
+    wtol = 5e-4 if dtype == torch.float32 else 1e-8
     mu_s = mu0.clone()
     for it in range(3):
         pre_means = mu_s.clone()
+        mu_f = mu_s.clone()
+        out = _ops().iterate(sh, desc, tab, spec['step_size'], 1, mu_f, seed=99, draw0=4 + it, want_samples=True)
         xs = _ops().sample(sh, tab, mu_s, seed=99, draw=4 + it)
         c = _ops().cost(sh, desc, tab, xs, mu_s)
         grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], c, xs, mu_s)
-    tol = 2e-4 if dtype == torch.float32 else 1e-9
-    assert float((out['means_pre'] - pre_means).abs().max() / pre_means.abs().max()) < tol
-    assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < tol
-    assert float((out['costs'] - c).abs().max() / c.abs().max()) < tol
-    assert float((out['weights'] - w).abs().max()) < (5e-3 if dtype == torch.float32 else 1e-8)
-    assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < (5e-3 if dtype == torch.float32 else 1e-8)
-    assert float((mu_f - mu_s).abs().max() / mu_s.abs().max()) < tol
+        assert torch.equal(out['means_pre'], pre_means)
+        assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < tol
+        assert float((out['costs'] - c).abs().max() / c.abs().max()) < tol
+        assert float((out['weights'] - w).abs().max()) < wtol
+        assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < 10 * wtol
+        assert float((mu_f - mu_s).abs().max() / mu_s.abs().max()) < 10 * wtol
+    if dtype == torch.float64:
+        mu_c = mu0.clone()
+        outc = _ops().iterate(sh, desc, tab, spec['step_size'], 3, mu_c, seed=99, draw0=4, want_samples=True)
+        assert float((mu_c - mu_s).abs().max() / mu_s.abs().max()) < 1e-7
+        assert float((outc['costs'] - c).abs().max() / c.abs().max()) < 1e-7
     ess = 1.0 / (w.double() ** 2).sum(-1)
     assert float(ess.max()) > 1.5          # the weighted pass really was exercised
 
