@@ -90,19 +90,19 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
 template int lower_cost_desc<float>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<float>&);
 template int lower_cost_desc<double>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<double>&);
 
-template <typename real, int N>
+template <typename real, int N, int CHAIN>
 __global__ void __launch_bounds__(128)
 cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int T,
             const double* __restrict__ tab, const real* __restrict__ samples, const real* __restrict__ means,
             real* __restrict__ costs, real* __restrict__ terms, size_t term_stride) {
     constexpr int d = 2 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tabDO = reinterpret_cast<double*>(smem_raw);                 // [T][7]
+    real* sph = reinterpret_cast<real*>(smem_raw);                       // [MAX_SPHERES][8] + coll_const
+    double* tabDO = reinterpret_cast<double*>(sph + SPH_SMEM);           // [T][7]
     real* bvec = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]
     real* mu = bvec + (size_t)T * d;                                     // [T][d]
     real* start = mu + (size_t)T * d;                                    // [d]
     real* goal = start + d;                                              // [d]
-    real* sph = goal + d;                                                // [O][4]
 
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
@@ -111,19 +111,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
             tabDO[k] = tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + SGPMP_TAB_D11 + (k % 7)];
     if (means)
         for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
-    for (int k = threadIdx.x; k < d; k += blockDim.x) {
-        start[k] = P.start[(size_t)b * d + k];
-        goal[k] = P.has_goal ? P.goals[((size_t)b * G + p / K) * d + k] : (real)0;
-    }
-    if (P.has_spheres)
-        for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x) {
-            const real* s4 = P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4;
-            sph[4 * k + 0] = s4[0]; sph[4 * k + 1] = s4[1]; sph[4 * k + 2] = s4[2];
-            const real r = s4[3];
-            sph[4 * k + 3] = (sizeof(real) == 4) ? (real)(-0.5 * 1.4426950408889634 / ((double)r * (double)r))
-                                                 : (real)(-0.5 / ((double)r * (double)r));
-        }
-    __syncthreads();
+    stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
     if (means) {
         for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
             const int t = k / N, i = k - t * N;
@@ -136,9 +124,10 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     if (s >= S) return;
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = means ? bvec : nullptr; sm.sph = sph;
+    sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
 
-    TrajCost<real, N> tc;
+    TrajCost<real, N, CHAIN> tc;
     tc.begin();
     const real* xs = samples + (size_t)bp * T * d * S + s;
     for (int t = 0; t < T; ++t) {
@@ -147,7 +136,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
         for (int j = 0; j < d; ++j) x[j] = xs[((size_t)t * d + j) * S];
         tc.step(P, sm, t, T, x);
     }
-    tc.finish(P);
+    tc.finish(P, sm, T);
     const size_t o = (size_t)bp * S + s;
     costs[o] = tc.total();
     if (terms) {
@@ -206,17 +195,17 @@ static int launch_fk(const sgpmp_cost_desc_t& desc, int n_dof, int n_cfg, const 
     return SGPMP_OK;
 }
 
-template <typename real, int N>
+template <typename real, int N, int CHAIN>
 static int launch_cost_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
                          const void* means, void* costs, void* terms, cudaStream_t st) {
     const int NP = sh.G * sh.K, d = 2 * N, bs = 128;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
-    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)2 * sh.T * d + 2 * d + 4 * SGPMP_MAX_SPHERES) * sizeof(real);
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)2 * sh.T * d + 2 * d + SPH_SMEM) * sizeof(real);
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) { set_error("sgpmp_cost: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
-        cudaFuncSetAttribute(cost_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cost_kernel<real, N, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    cost_kernel<real, N><<<grid, bs, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
+    cost_kernel<real, N, CHAIN><<<grid, bs, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
                                                   (const real*)means, (real*)costs, (real*)terms,
                                                   (size_t)sh.B * NP * sh.S);
     SGPMP_CHECK_LAUNCH("sgpmp_cost");
@@ -229,8 +218,12 @@ static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
     CostParams<real> P;
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
+    if constexpr (sizeof(real) == 4) {
+        if (P.has_spheres && chain_is_panda_structure(desc, sh.n_dof))
+            return launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
+    }
     switch (sh.n_dof) {
-#define SGPMP_DOF_CASE(N) case N: return launch_cost_n<real, N>(sh, P, tables, samples, means, costs, terms, st);
+#define SGPMP_DOF_CASE(N) case N: return launch_cost_n<real, N, 0>(sh, P, tables, samples, means, costs, terms, st);
 #include "sgpmp_dof_list.inc"
 #undef SGPMP_DOF_CASE
         default:

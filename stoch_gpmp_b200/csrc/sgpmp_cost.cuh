@@ -12,6 +12,8 @@
 //   FK hook                      costs/cost_functions.py:51-52 (torch_robotics chain, restated from the URDF)
 //   IS term                      planner.py:233-236   tau * x^T Sigma^-1 mu  ==  tau * sum_t x_t . b_t, b = P mu
 #pragma once
+#include <math.h>
+
 #include "sgpmp_common.cuh"
 
 namespace sgpmp {
@@ -32,9 +34,33 @@ struct CostSmem {
     const real* start;   // [d]
     const real* goal;    // [d] goal of this particle (or null)
     const real* bvec;    // [T][d]   b = Sigma^-1 mu of this particle
-    const real* sph;     // [O][4]   (cx, cy, cz, kexp) kexp = -0.5/r^2 (* log2 e in fp32)
+    const real* sph;     // [O][8]   (cx, cy, cz, k, ax, ay, az, b): k = -0.5/r^2 (* log2 e in fp32),
+                         //          a = -2 k c, b = k |c|^2  so that  k |p - c|^2 = k |p|^2 + a.p + b
     const real* map;     // occupancy map of this problem (global memory)
+    real coll_const;     // RBF sum of the link frames whose position does not depend on q (structured chains)
 };
+
+constexpr int SPH_STRIDE = 8;
+
+// 4 consecutive reals from a 16-byte (fp32) / 32-byte (fp64) aligned shared-memory address in one LDS
+__device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double& a, double& b, double& c, double& d) {
+    const double2 v = *reinterpret_cast<const double2*>(p), w = *reinterpret_cast<const double2*>(p + 2);
+    a = v.x; b = v.y; c = w.x; d = w.y;
+}
+
+// Stage one sphere (cx, cy, cz, r) into the shared table row.
+template <typename real>
+__device__ __forceinline__ void stage_sphere(const real* s4, real* row) {
+    const double cx = s4[0], cy = s4[1], cz = s4[2], r = s4[3];
+    const double k = (sizeof(real) == 4 ? -0.5 * 1.4426950408889634 : -0.5) / (r * r);
+    row[0] = (real)cx; row[1] = (real)cy; row[2] = (real)cz; row[3] = (real)k;
+    row[4] = (real)(-2.0 * k * cx); row[5] = (real)(-2.0 * k * cy); row[6] = (real)(-2.0 * k * cz);
+    row[7] = (real)(k * (cx * cx + cy * cy + cz * cz));
+}
 
 // Forward kinematics of a serial arm (frames 0..N-1: fixed transform then revolute-z joint f; frames
 // N..n_frames-1 fixed), calling visit(x, y, z) for every link-frame origin in chain order
@@ -78,7 +104,75 @@ __device__ __forceinline__ void fk_visit_links(const CostParams<real>& P, const 
     }
 }
 
-template <typename real, int N>
+// ---- structured chains ------------------------------------------------------------------------------
+// CHAIN = 0: generic serial arm (fk_visit_links, runtime constants).
+// CHAIN = 1: "Panda structure" (7 joints): fixed rotations are identity / Rx(+-90 deg) / about-z, and most
+// translation components are zero (panda_arm_no_gripper.urdf).  The STRUCTURE is compile-time — Rx(+-90)
+// becomes a signed relabelling of columns, zero translation components vanish — while the translation VALUES
+// still come from the descriptor.  The host selects it only when the descriptor matches this structure
+// (cos(1.57079632679) = 4.9e-12 is below fp32 resolution; fp64 always uses the generic path).
+// Further structure used: frames with zero translation share their parent's origin (evaluated once, weight
+// 2); origins that do not depend on q (base, link1, link2) are folded into CostSmem::coll_const; joint 7 only
+// spins the z axis along which the remaining translations point, so q[6] is never needed.
+constexpr int PANDA_EVAL_LINKS = 6;   // link3, link4, link5(=link6), link7, link8(=hand), ee
+
+template <typename real>
+struct Cols {   // rotation columns
+    real ax, ay, az, bx, by, bz, cx, cy, cz;
+    __device__ __forceinline__ void rot_xp90() {   // R <- R Rx(+90): (a, b, c) -> (a, c, -b)
+        const real tx = bx, ty = by, tz = bz;
+        bx = cx; by = cy; bz = cz;
+        cx = -tx; cy = -ty; cz = -tz;
+    }
+    __device__ __forceinline__ void rot_xm90() {   // R <- R Rx(-90): (a, b, c) -> (a, -c, b)
+        const real tx = bx, ty = by, tz = bz;
+        bx = -cx; by = -cy; bz = -cz;
+        cx = tx; cy = ty; cz = tz;
+    }
+    __device__ __forceinline__ void rot_z(real q) {  // R <- R Rz(q)
+        real s, c;
+        sg_sincos(q, &s, &c);
+        const real nax = c * ax + s * bx, nay = c * ay + s * by, naz = c * az + s * bz;
+        bx = c * bx - s * ax; by = c * by - s * ay; bz = c * bz - s * az;
+        ax = nax; ay = nay; az = naz;
+    }
+};
+
+// Origins of the 6 q-dependent, distinct link frames of the Panda structure; weights {1,1,2,1,2,1}.
+template <typename real>
+__device__ __forceinline__ void fk_panda_origins(const CostParams<real>& P, const real* q, real (&X)[PANDA_EVAL_LINKS],
+                                                 real (&Y)[PANDA_EVAL_LINKS], real (&Z)[PANDA_EVAL_LINKS]) {
+    Cols<real> R{1, 0, 0, 0, 1, 0, 0, 0, 1};
+    real px = 0, py = 0, pz = P.p[0][2];           // frame 0: t = (0,0,z), rot = I
+    R.rot_z(q[0]);
+    R.rot_xm90();                                  // frame 1: t = 0, Rx(-90)
+    R.rot_z(q[1]);
+    px += P.p[2][1] * R.bx; py += P.p[2][1] * R.by; pz += P.p[2][1] * R.bz;   // frame 2: t = (0,y,0), Rx(+90)
+    X[0] = px; Y[0] = py; Z[0] = pz;               // link3
+    R.rot_xp90();
+    R.rot_z(q[2]);
+    px += P.p[3][0] * R.ax; py += P.p[3][0] * R.ay; pz += P.p[3][0] * R.az;   // frame 3: t = (x,0,0), Rx(+90)
+    X[1] = px; Y[1] = py; Z[1] = pz;               // link4
+    R.rot_xp90();
+    R.rot_z(q[3]);
+    px += P.p[4][0] * R.ax + P.p[4][1] * R.bx;                                 // frame 4: t = (x,y,0), Rx(-90)
+    py += P.p[4][0] * R.ay + P.p[4][1] * R.by;
+    pz += P.p[4][0] * R.az + P.p[4][1] * R.bz;
+    X[2] = px; Y[2] = py; Z[2] = pz;               // link5 (= link6: frame 5 has t = 0)
+    R.rot_xm90();
+    R.rot_z(q[4]);
+    R.rot_xp90();                                  // frame 5: t = 0, Rx(+90)
+    R.rot_z(q[5]);
+    px += P.p[6][0] * R.ax; py += P.p[6][0] * R.ay; pz += P.p[6][0] * R.az;   // frame 6: t = (x,0,0), Rx(+90)
+    X[3] = px; Y[3] = py; Z[3] = pz;               // link7
+    R.rot_xp90();                                  // joint 7 spins about c: c unchanged, q[6] not needed
+    px += P.p[7][2] * R.cx; py += P.p[7][2] * R.cy; pz += P.p[7][2] * R.cz;   // frame 7: t = (0,0,z)
+    X[4] = px; Y[4] = py; Z[4] = pz;               // link8 (= hand: frame 8 has t = 0, rotation about z)
+    px += P.p[9][2] * R.cx; py += P.p[9][2] * R.cy; pz += P.p[9][2] * R.cz;   // frame 9: t = (0,0,z), about z
+    X[5] = px; Y[5] = py; Z[5] = pz;               // ee_link
+}
+
+template <typename real, int N, int CHAIN = 0>
 struct TrajCost {
     real c_start, c_gp, c_goal, c_coll, c_is;
     real xp[2 * N];   // previous state
@@ -90,12 +184,34 @@ struct TrajCost {
                                                     const real* q) const {
         real acc = 0;
         const int O = P.n_spheres;
-        fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+        if constexpr (CHAIN == 1) {
+            static_assert(N == 7, "Panda structure has 7 joints");
+            real X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS], PP[PANDA_EVAL_LINKS];
+            fk_panda_origins<real>(P, q, X, Y, Z);
+#pragma unroll
+            for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = X[l] * X[l] + Y[l] * Y[l] + Z[l] * Z[l];
+            real acc2 = 0;   // links with weight 2
             for (int o = 0; o < O; ++o) {
-                const real dx = x - sm.sph[4 * o + 0], dy = y - sm.sph[4 * o + 1], dz = z - sm.sph[4 * o + 2];
-                acc += rbf_exp(sm.sph[4 * o + 3], dx * dx + dy * dy + dz * dz);
+                const real* s = sm.sph + SPH_STRIDE * o;
+                const real k = s[3];
+                real ax, ay, az, b;
+                load4(s + 4, ax, ay, az, b);
+#pragma unroll
+                for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
+                    const real e = rbf_exp((real)1, X[l] * ax + (Y[l] * ay + (Z[l] * az + (k * PP[l] + b))));
+                    if (l == 2 || l == 4) acc2 += e; else acc += e;
+                }
             }
-        });
+            acc += acc2 + acc2;
+        } else {
+            fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+                for (int o = 0; o < O; ++o) {
+                    const real* s = sm.sph + SPH_STRIDE * o;
+                    const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
+                    acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
+                }
+            });
+        }
         return acc;
     }
 
@@ -145,15 +261,71 @@ struct TrajCost {
         for (int j = 0; j < 2 * N; ++j) xp[j] = x[j];
     }
 
-    __device__ __forceinline__ void finish(const CostParams<real>& P) {
+    __device__ __forceinline__ void finish(const CostParams<real>& P, const CostSmem<real>& sm, int T) {
         c_start *= P.inv_sig_start2;
         c_goal *= P.inv_sig_goal2;
+        if (CHAIN == 1) c_coll += (real)(T - 1) * sm.coll_const;
         c_coll *= (P.has_map ? P.map_w_coll : P.sphere_w_coll);
         c_is *= P.temperature;
     }
     // reference summation order: CostGP (start + gp), CostGoalPrior, CostCollision, then += IS
     __device__ __forceinline__ real total() const { return (((c_start + c_gp) + c_goal) + c_coll) + c_is; }
 };
+
+// Per-CTA staging of the problem constants into shared memory: start [d], goal [d] of goal index g, the sphere
+// table [MAX_SPHERES][8] followed by one slot for coll_const.  Ends with a __syncthreads().
+constexpr int SPH_SMEM = SPH_STRIDE * SGPMP_MAX_SPHERES + 4;   // keeps what follows 16-byte aligned
+
+template <typename real, int N, int CHAIN>
+__device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, int b, int g, int G, real* start, real* goal,
+                                                    real* sph) {
+    constexpr int d = 2 * N;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        start[k] = P.start[(size_t)b * d + k];
+        goal[k] = P.has_goal ? P.goals[((size_t)b * G + g) * d + k] : (real)0;
+    }
+    if (P.has_spheres)
+        for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x)
+            stage_sphere<real>(P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4, sph + SPH_STRIDE * k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        real cc = 0;
+        if (CHAIN == 1 && P.has_spheres) {
+            // q-independent origins of the Panda structure: base (if counted), link1 and link2 at (0, 0, z0)
+            const real z0 = P.p[0][2];
+            for (int o = 0; o < P.n_spheres; ++o) {
+                const real* s = sph + SPH_STRIDE * o;
+                if (P.include_base) cc += rbf_exp((real)1, s[7]);
+                cc += (real)2 * rbf_exp((real)1, z0 * s[6] + (s[3] * z0 * z0 + s[7]));
+            }
+        }
+        sph[SPH_STRIDE * SGPMP_MAX_SPHERES] = cc;
+    }
+    __syncthreads();
+}
+
+// 1 if the descriptor's chain has the Panda STRUCTURE (see fk_panda_origins); host-side check.
+inline int chain_is_panda_structure(const sgpmp_cost_desc_t& d, int n_dof) {
+    if (n_dof != 7 || d.n_frames != 10) return 0;
+    static const int rot[10] = {0, -1, 1, 1, -1, 1, 1, 0, 2, 2};          // 0: I, +-1: Rx(+-90), 2: about z
+    static const int tmask[10] = {4, 0, 2, 1, 3, 0, 1, 4, 0, 4};          // bit0 x, bit1 y, bit2 z may be non-zero
+    const double tol = 1e-9;
+    for (int f = 0; f < 10; ++f) {
+        const double* R = d.chain_R[f];
+        for (int k = 0; k < 3; ++k)
+            if (!((tmask[f] >> k) & 1) && d.chain_p[f][k] != 0.0) return 0;
+        double want[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (rot[f] == 1) { double w[9] = {1, 0, 0, 0, 0, -1, 0, 1, 0}; memcpy(want, w, sizeof(w)); }
+        if (rot[f] == -1) { double w[9] = {1, 0, 0, 0, 0, 1, 0, -1, 0}; memcpy(want, w, sizeof(w)); }
+        if (rot[f] == 2) {   // rotation about z: third row/column are e_z
+            if (fabs(R[2]) > tol || fabs(R[5]) > tol || fabs(R[6]) > tol || fabs(R[7]) > tol || fabs(R[8] - 1) > tol) return 0;
+            continue;
+        }
+        for (int k = 0; k < 9; ++k)
+            if (fabs(R[k] - want[k]) > tol) return 0;
+    }
+    return 1;
+}
 
 // b = P mu for one particle, computed in fp64 from the D/O blocks (the fp32 reference evaluates this
 // contraction with catastrophic cancellation), stored as `real`.

@@ -38,7 +38,7 @@ struct IterArgs {
     real* grad;            // optional, last iteration
 };
 
-template <typename real, int N, int BS>
+template <typename real, int N, int BS, int CHAIN>
 __global__ void __launch_bounds__(BS)
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
     constexpr int d = 2 * N;
@@ -46,7 +46,8 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     const int TP = (T + 1) >> 1;
     const int M = T * d;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tabDO = reinterpret_cast<double*>(smem_raw);     // [T][7]
+    real* sph = reinterpret_cast<real*>(smem_raw);            // [MAX_SPHERES][8] + coll_const (16-byte aligned)
+    double* tabDO = reinterpret_cast<double*>(sph + SPH_SMEM);   // [T][7]
     real* tabGH = reinterpret_cast<real*>(tabDO + (size_t)T * 7);   // [T][7]
     real* mu = tabGH + (size_t)T * 7;                         // [T][d]
     real* bvec = mu + M;                                      // [T][d]
@@ -56,7 +57,6 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     real* red = part + 4 * BS;                                // [32]
     real* start = red + 32;                                   // [d]
     real* goal = start + d;                                   // [d]
-    real* sph = goal + d;                                     // [4*MAX_SPHERES]
 
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
@@ -69,20 +69,10 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         tabDO[k] = row[SGPMP_TAB_D11 + (k % 7)];
     }
     for (int k = tid; k < M; k += BS) mu[k] = A.means[(size_t)bp * M + k];
-    for (int k = tid; k < d; k += BS) {
-        start[k] = P.start[(size_t)b * d + k];
-        goal[k] = P.has_goal ? P.goals[((size_t)b * G + p / K) * d + k] : (real)0;
-    }
-    if (P.has_spheres)
-        for (int k = tid; k < P.n_spheres; k += BS) {
-            const real* s4 = P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4;
-            sph[4 * k + 0] = s4[0]; sph[4 * k + 1] = s4[1]; sph[4 * k + 2] = s4[2];
-            const real r = s4[3];
-            sph[4 * k + 3] = (sizeof(real) == 4) ? (real)(-0.5 * 1.4426950408889634 / ((double)r * (double)r))
-                                                 : (real)(-0.5 / ((double)r * (double)r));
-        }
+    stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = bvec; sm.sph = sph;
+    sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     __syncthreads();
 
@@ -104,7 +94,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         // ---- pass 1: sample + cost, one thread per trajectory sample -----------------------------------
         const bool emit = last && A.samples != nullptr;
         for (int s = tid; s < S; s += BS) {
-            TrajCost<real, N> tc;
+            TrajCost<real, N, CHAIN> tc;
             tc.begin();
             real yp[N], yv[N];
 #pragma unroll
@@ -145,7 +135,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                     }
                 }
             }
-            tc.finish(P);
+            tc.finish(P, sm, T);
             const real c = tc.total();
             wsm[s] = c;
             if (last && A.costs) A.costs[(size_t)bp * S + s] = c;
@@ -258,26 +248,26 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[k];
 }
 
-template <typename real, int N, int BS>
+template <typename real, int N, int BS, int CHAIN>
 static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
     const int d = 2 * N, M = sh.T * d;
     const size_t smem = (size_t)sh.T * 7 * sizeof(double) +
-                        ((size_t)sh.T * 7 + 3 * (size_t)M + sh.S + 4 * BS + 32 + 2 * d + 4 * SGPMP_MAX_SPHERES) * sizeof(real);
+                        ((size_t)sh.T * 7 + 3 * (size_t)M + sh.S + 4 * BS + 32 + 2 * d + SPH_SMEM) * sizeof(real);
     if (smem > 227 * 1024) {
         set_error("sgpmp_iterate: T=%d, S=%d need %zu bytes of shared memory (> 227 KiB)", sh.T, sh.S, smem);
         return SGPMP_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(iterate_kernel<real, N, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    iterate_kernel<real, N, BS><<<(unsigned)(sh.B * sh.G * sh.K), BS, smem, st>>>(P, A);
+        cudaFuncSetAttribute(iterate_kernel<real, N, BS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    iterate_kernel<real, N, BS, CHAIN><<<(unsigned)(sh.B * sh.G * sh.K), BS, smem, st>>>(P, A);
     SGPMP_CHECK_LAUNCH("sgpmp_iterate");
     return SGPMP_OK;
 }
 
-template <typename real, int N>
+template <typename real, int N, int CHAIN>
 static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
-    if (sh.S > 128) return launch_iterate_nb<real, N, 256>(sh, P, A, st);
-    return launch_iterate_nb<real, N, 128>(sh, P, A, st);
+    if (sh.S > 128) return launch_iterate_nb<real, N, 256, CHAIN>(sh, P, A, st);
+    return launch_iterate_nb<real, N, 128, CHAIN>(sh, P, A, st);
 }
 
 template <typename real>
@@ -297,8 +287,11 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     A.eps_in = (const real*)eps_in;
     A.means = (real*)means; A.means_pre = (real*)means_pre; A.samples = (real*)samples;
     A.costs = (real*)costs; A.weights = (real*)weights; A.grad = (real*)grad;
+    if constexpr (sizeof(real) == 4) {
+        if (P.has_spheres && chain_is_panda_structure(desc, sh.n_dof)) return launch_iterate_n<real, 7, 1>(sh, P, A, st);
+    }
     switch (sh.n_dof) {
-#define SGPMP_DOF_CASE(N) case N: return launch_iterate_n<real, N>(sh, P, A, st);
+#define SGPMP_DOF_CASE(N) case N: return launch_iterate_n<real, N, 0>(sh, P, A, st);
 #include "sgpmp_dof_list.inc"
 #undef SGPMP_DOF_CASE
         default:

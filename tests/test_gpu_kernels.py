@@ -157,9 +157,10 @@ def test_sample_inkernel_rng_matches_oracle_stream(dtype, T, n, S, cuda):
     if dtype == torch.float64:
         assert np.abs(eps - want).max() < 1e-12
     else:
-        # fp32 rounds (w + 0.5) 2^-32 to 24 bits: |d eps| <~ 3e-6 except in the vanishing-r corner u1 -> 1
+        # fp32 uses the MUFU forms (lg2/sqrt/sin/cos.approx) and rounds (w + 0.5) 2^-32 to 24 bits:
+        # |d eps| <~ 5e-6 except in the vanishing-radius corner u1 -> 1
         err = np.abs(eps - want)
-        assert np.quantile(err, 0.999) < 5e-6 and err.max() < 2e-3
+        assert np.quantile(err, 0.999) < 2e-5 and err.max() < 5e-3
     _, _, fac = OP.sampling_prior(dict(spec, n_dof=n))
     y = SMP.banded_transform(fac['G'], fac['H'], eps.astype(np.float64))
     assert rel(from_sminor(x.cpu().numpy()), y) < (1e-12 if dtype == torch.float64 else 2e-6)
