@@ -99,40 +99,36 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             real yp[N], yv[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) { yp[i] = 0; yv[i] = 0; }
-            for (int tp = 0; tp < TP; ++tp) {
-                real e[2][d];
+            // One Philox call per DoF yields the normals of TWO time steps; the step body is kept as a single
+            // (not 2x unrolled) copy so that the hot loop stays inside the instruction cache.
+            real en[d];
+#pragma unroll 1
+            for (int t = 0; t < T; ++t) {
+                real e[d];
                 if (eps) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int t = 2 * tp + h;
+                    for (int j = 0; j < d; ++j) e[j] = eps[((size_t)t * d + j) * S + s];
+                } else if ((t & 1) == 0) {
 #pragma unroll
-                        for (int j = 0; j < d; ++j) e[h][j] = (t < T) ? eps[((size_t)t * d + j) * S + s] : (real)0;
-                    }
+                    for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, s, pgid, e[i], e[N + i], en[i], en[N + i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < N; ++i)
-                        normal4<real>(key, tp, i, s, pgid, e[0][i], e[0][N + i], e[1][i], e[1][N + i]);
+                    for (int j = 0; j < d; ++j) e[j] = en[j];
                 }
+                const real* r = tabGH + t * 7;
+                real x[d];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int t = 2 * tp + h;
-                    if (t < T) {
-                        const real* r = tabGH + t * 7;
-                        real x[d];
+                for (int i = 0; i < N; ++i) {
+                    const real np_ = r[0] * e[i] - (r[3] * yp[i] + r[4] * yv[i]);
+                    const real nv_ = r[1] * e[i] + r[2] * e[N + i] - (r[5] * yp[i] + r[6] * yv[i]);
+                    yp[i] = np_; yv[i] = nv_;
+                    x[i] = mu[t * d + i] + np_;
+                    x[N + i] = mu[t * d + N + i] + nv_;
+                }
+                tc.step(P, sm, t, T, x);
+                if (emit) {
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            const real np_ = r[0] * e[h][i] - (r[3] * yp[i] + r[4] * yv[i]);
-                            const real nv_ = r[1] * e[h][i] + r[2] * e[h][N + i] - (r[5] * yp[i] + r[6] * yv[i]);
-                            yp[i] = np_; yv[i] = nv_;
-                            x[i] = mu[t * d + i] + np_;
-                            x[N + i] = mu[t * d + N + i] + nv_;
-                        }
-                        tc.step(P, sm, t, T, x);
-                        if (emit) {
-#pragma unroll
-                            for (int j = 0; j < d; ++j) A.samples[((size_t)bp * M + (size_t)t * d + j) * S + s] = x[j];
-                        }
-                    }
+                    for (int j = 0; j < d; ++j) A.samples[((size_t)bp * M + (size_t)t * d + j) * S + s] = x[j];
                 }
             }
             tc.finish(P, sm, T);
