@@ -32,7 +32,7 @@ ts=sum(samp.values())
 print('--- SASS opcode mix (warp instructions executed: %d)'%tot)
 for op,c in ops.most_common(16): print('%-10s %6.2f%% inst   %6.2f%% stall samples'%(op,100*c/tot,100*samp[op]/ts))
 PY
-D=$(mktemp -d); (cd $D && cuobjdump -xelf all $(dirname $0)/../stoch_gpmp_b200/_C/libsgpmp.so >/dev/null 2>&1)
+D=$(mktemp -d); HERE=$(cd $(dirname $0) && pwd); (cd $D && cuobjdump -xelf all $HERE/../stoch_gpmp_b200/_C/libsgpmp.so >/dev/null 2>&1)
 for f in $D/*.cubin; do if nvdisasm -g -c $f 2>/dev/null | grep -q "$KN"; then nvdisasm -g -c $f > $TMP/k.sass; fi; done
 echo "--- per source line"
-python $(dirname $0)/attribute_lines.py $TMP/src.csv $TMP/k.sass $KN 28
+python $HERE/attribute_lines.py $TMP/src.csv $TMP/k.sass $KN 28

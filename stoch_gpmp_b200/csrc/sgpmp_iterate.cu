@@ -16,9 +16,18 @@
 //     banded recurrence per DoF applies L.  mu and b = Sigma^-1 mu stay in shared memory across
 //     iterations; particles are independent, so no grid-wide synchronisation exists anywhere.
 //   * FP32-pipe/MUFU bound; HBM traffic is O(NP*M) per iteration instead of 3*M*S*NP.
+#include <stdlib.h>
+
 #include "sgpmp_common.cuh"
 #include "sgpmp_cost.cuh"
 #include "sgpmp_rng.cuh"
+
+#ifndef SGPMP_MINB128
+#define SGPMP_MINB128 5
+#endif
+#ifndef SGPMP_MINB256
+#define SGPMP_MINB256 3
+#endif
 
 namespace sgpmp {
 
@@ -39,7 +48,7 @@ struct IterArgs {
 };
 
 template <typename real, int N, int BS, int CHAIN>
-__global__ void __launch_bounds__(BS)
+__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (BS == 128 ? SGPMP_MINB128 : SGPMP_MINB256) : 1))
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
     constexpr int d = 2 * N;
     const int T = A.T, S = A.S, G = A.G, K = A.K;
@@ -262,7 +271,8 @@ static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P,
 
 template <typename real, int N, int CHAIN>
 static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
-    if (sh.S > 128) return launch_iterate_nb<real, N, 256, CHAIN>(sh, P, A, st);
+    static const char* force_bs = getenv("SGPMP_ITERATE_BS");   // tuning aid
+    if (sh.S > 128 && !(force_bs && atoi(force_bs) == 128)) return launch_iterate_nb<real, N, 256, CHAIN>(sh, P, A, st);
     return launch_iterate_nb<real, N, 128, CHAIN>(sh, P, A, st);
 }
 
