@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Per-kernel roofline measurements of the standalone (materialising) path: K1 prior, K2 sample, K3 cost,
+K4 update, and the split-mode statistics kernels — the numbers DESIGN.md §4 quotes next to the fused kernel.
+
+    python bench_kernels.py [--workload panda|planar] [--problems 1024] [--reps 10]
+
+Prints one JSON line per kernel: algorithmic bytes / flops per launch, CUDA-event time
+(median of --reps, L2 flushed between launches), achieved GB/s or TFLOP/s and the fraction of the measured
+peak (MEASURED_PEAKS.json HBM copy bandwidth; FP32 FMA probe for the FP32-bound kernel).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="panda", choices=["panda", "planar"])
+    ap.add_argument("--problems", type=int, default=1024)
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    import torch
+    import bench
+    from stoch_gpmp_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B = args.problems
+    w = bench.workload(args.workload, B)
+    pl = bench.build_planner(w, B, dev)
+    n, T, G, K, S = w["n_dof"], w["T"], w["G"], w["K"], w["S"]
+    NP, d = G * K, 2 * n
+    M = T * d
+    ntraj = B * NP * S
+    obs = {"obstacle_spheres": torch.tensor(w["spheres"], dtype=torch.float32, device=dev)} if w["spheres"] is not None else {}
+    desc = pl._desc(obs)
+    sh = pl._shape()
+    tab = pl._tables
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    peaks = bench.probe_peaks(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def timeit(fn):
+        ts = []
+        for _ in range(3):
+            fn()
+        for _ in range(args.reps):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def report(name, ms, bytes_=None, flops=None, note=""):
+        line = {"kernel": name, "workload": w["name"], "problems": B, "traj_samples": ntraj, "ms": ms, "note": note}
+        if bytes_ is not None:
+            gbs = bytes_ / (ms * 1e-3) / 1e9
+            line.update(bound="hbm", algorithmic_bytes=bytes_, achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm)
+        if flops is not None:
+            tf = flops / (ms * 1e-3) / 1e12
+            line.update(bound="fp32", algorithmic_flops=flops, achieved_tflops=tf, peak_tflops=peaks["fp32_tflops"], frac=tf / peaks["fp32_tflops"])
+        print(json.dumps(line), flush=True)
+
+    means = pl._means.clone()
+    xs, eps = ops.sample(sh, tab, means, seed=1, draw=0, want_eps=True)
+    # K2 with in-kernel RNG: writes M*w per sample
+    out = torch.empty_like(xs)
+
+    def k2_rng():
+        ops._lib.check(ops._lib.load().sgpmp_sample(ops.C.byref(sh), ops._ptr(tab), ops._ptr(means), None, 1, 0, ops._ptr(out), None, ops._stream()), "k2")
+    report("K2 sample (in-kernel Philox)", timeit(k2_rng), bytes_=ntraj * M * 4, note="writes M*4 B per trajectory sample")
+
+    def k2_inj():
+        ops._lib.check(ops._lib.load().sgpmp_sample(ops.C.byref(sh), ops._ptr(tab), ops._ptr(means), ops._ptr(eps), 1, 0, ops._ptr(out), None, ops._stream()), "k2")
+    report("K2 sample (injected eps)", timeit(k2_inj), bytes_=2 * ntraj * M * 4, note="reads eps + writes samples")
+
+    costs = torch.empty(B, NP, S, device=dev)
+
+    def k3():
+        ops._lib.check(ops._lib.load().sgpmp_cost(ops.C.byref(sh), ops.C.byref(desc), ops._ptr(tab), ops._ptr(xs), ops._ptr(means), ops._ptr(costs), None, ops._stream()), "k3")
+    f_cost, _ = bench.algorithmic_flops_per_traj(w)
+    f_cost -= 16 * T * n + 2 * M + 10      # minus sampling recurrence and softmax/update
+    ms3 = timeit(k3)
+    report("K3 cost", ms3, flops=ntraj * f_cost, note="FP32-bound for Panda")
+    report("K3 cost (as HBM stream)", ms3, bytes_=ntraj * (M + 1) * 4, note="reads M*4 B per trajectory sample")
+
+    grad = torch.empty_like(means)
+    wts = torch.empty_like(costs)
+    mu2 = means.clone()
+
+    def k4():
+        ops._lib.check(ops._lib.load().sgpmp_update(ops.C.byref(sh), float(w["temperature"]), float(w["step_size"]), ops._ptr(costs), ops._ptr(xs), ops._ptr(mu2), ops._ptr(grad), ops._ptr(wts), ops._stream()), "k4")
+    report("K4 update", timeit(k4), bytes_=ntraj * (M + 2) * 4, note="reads samples + costs, writes weights")
+
+    def k_stats():
+        ops.local_stats(sh, w["temperature"], costs, eps)
+    report("local_stats (split mode)", timeit(k_stats), bytes_=ntraj * (M + 1) * 4)
+
+    # K1: latency
+    from stoch_gpmp_b200.planner import prior_blocks
+    for TT in (64, 1024):
+        D, O = prior_blocks(TT, w["dt"], w["sig"]["sigma_start_sample"], w["sig"]["sigma_gp_sample"], w["sig"]["sigma_goal_sample"])
+        Dt = torch.tensor([D], dtype=torch.float64, device=dev)
+        Ot = torch.tensor([O], dtype=torch.float64, device=dev)
+        report("K1 prior factor T=%d" % TT, timeit(lambda: ops.prior_factor(Dt, Ot)), note="latency-bound, one thread per prior (includes two small torch allocations)")
+
+
+if __name__ == "__main__":
+    main()

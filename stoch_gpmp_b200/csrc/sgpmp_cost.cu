@@ -96,11 +96,12 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
             const double* __restrict__ tab, const real* __restrict__ samples, const real* __restrict__ means,
             real* __restrict__ costs, real* __restrict__ terms, size_t term_stride) {
     constexpr int d = 2 * N;
+    constexpr int DP = (d + 3) & ~3;      // padded row length: rows stay 16-byte aligned for LDS.128
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* sph = reinterpret_cast<real*>(smem_raw);                       // [MAX_SPHERES][8] + coll_const
-    double* tabDO = reinterpret_cast<double*>(sph + SPH_SMEM);           // [T][7]
-    real* bvec = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]
-    real* mu = bvec + (size_t)T * d;                                     // [T][d]
+    real* bvec = sph + SPH_SMEM;                                         // [T][DP]
+    double* tabDO = reinterpret_cast<double*>(bvec + (size_t)T * DP);    // [T][7]
+    real* mu = reinterpret_cast<real*>(tabDO + (size_t)T * 7);           // [T][d]
     real* start = mu + (size_t)T * d;                                    // [d]
     real* goal = start + d;                                              // [d]
 
@@ -115,7 +116,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     if (means) {
         for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
             const int t = k / N, i = k - t * N;
-            precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * d + i], &bvec[t * d + N + i]);
+            precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
         }
     }
     __syncthreads();
@@ -134,7 +135,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
         real x[d];
 #pragma unroll
         for (int j = 0; j < d; ++j) x[j] = xs[((size_t)t * d + j) * S];
-        tc.step(P, sm, t, T, x);
+        tc.step(P, sm, t, T, x, means ? bvec + t * DP : nullptr);
     }
     tc.finish(P, sm, T);
     const size_t o = (size_t)bp * S + s;
@@ -200,7 +201,7 @@ static int launch_cost_n(const sgpmp_shape_t& sh, const CostParams<real>& P, con
                          const void* means, void* costs, void* terms, cudaStream_t st) {
     const int NP = sh.G * sh.K, d = 2 * N, bs = 128;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
-    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)2 * sh.T * d + 2 * d + SPH_SMEM) * sizeof(real);
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM) * sizeof(real);
     if (smem > 48 * 1024) {
         if (smem > 227 * 1024) { set_error("sgpmp_cost: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
         cudaFuncSetAttribute(cost_kernel<real, N, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

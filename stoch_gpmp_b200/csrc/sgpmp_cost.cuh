@@ -227,8 +227,9 @@ struct TrajCost {
     }
 
     // feed state x_t (t = 0..T-1 in order)
+    // brow: b_t = (Sigma^-1 mu)_t of this particle (2N reals, 16-byte aligned when 2N % 4 == 0 rows are padded), or null
     __device__ __forceinline__ void step(const CostParams<real>& P, const CostSmem<real>& sm, int t, int T,
-                                         const real (&x)[2 * N]) {
+                                         const real (&x)[2 * N], const real* brow) {
         if (t == 0) {
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) {
@@ -252,8 +253,11 @@ struct TrajCost {
                 c_goal += e * e;
             }
         }
-        if (sm.bvec) {
-            const real* b = sm.bvec + (size_t)t * 2 * N;
+        if (brow) {
+            constexpr int DP4 = (2 * N + 3) / 4;
+            real b[4 * DP4];
+#pragma unroll
+            for (int k = 0; k < DP4; ++k) load4(brow + 4 * k, b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) c_is += x[j] * b[j];
         }
@@ -330,10 +334,11 @@ inline int chain_is_panda_structure(const sgpmp_cost_desc_t& d, int n_dof) {
 // b = P mu for one particle, computed in fp64 from the D/O blocks (the fp32 reference evaluates this
 // contraction with catastrophic cancellation), stored as `real`.
 // tabDO: [T][7] doubles (d11,d12,d22,o11,o12,o21,o22), O_t = P[t+1,t].
-template <typename real>
+// MU_STRIDE: row stride of mu in reals (0 = dense rows of 2n).
+template <typename real, int MU_STRIDE = 0>
 __device__ __forceinline__ void precision_times_row(const double* tabDO, const real* mu, int T, int n, int t, int i,
                                                     real* bp, real* bv) {
-    const int d = 2 * n;
+    const int d = MU_STRIDE ? MU_STRIDE : 2 * n;
     const double* r = tabDO + t * 7;
     const double mp = mu[t * d + i], mv = mu[t * d + n + i];
     double p = r[0] * mp + r[1] * mv;

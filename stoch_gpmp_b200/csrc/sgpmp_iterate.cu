@@ -51,16 +51,17 @@ template <typename real, int N, int BS, int CHAIN>
 __global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (BS == 128 ? SGPMP_MINB128 : SGPMP_MINB256) : 1))
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
     constexpr int d = 2 * N;
+    constexpr int DP = (d + 3) & ~3;      // padded row length of mu / b: rows stay 16-byte aligned for LDS.128
     const int T = A.T, S = A.S, G = A.G, K = A.K;
     const int TP = (T + 1) >> 1;
     const int M = T * d;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* sph = reinterpret_cast<real*>(smem_raw);            // [MAX_SPHERES][8] + coll_const (16-byte aligned)
-    double* tabDO = reinterpret_cast<double*>(sph + SPH_SMEM);   // [T][7]
-    real* tabGH = reinterpret_cast<real*>(tabDO + (size_t)T * 7);   // [T][7]
-    real* mu = tabGH + (size_t)T * 7;                         // [T][d]
-    real* bvec = mu + M;                                      // [T][d]
-    real* acc = bvec + M;                                     // [T][d]  sum_s w_s eps_s, then grad
+    real* tabGH = sph + SPH_SMEM;                             // [T][8]  (g11 g21 g22 h11 | h12 h21 h22 -)
+    real* mu = tabGH + (size_t)T * 8;                         // [T][DP]
+    real* bvec = mu + (size_t)T * DP;                         // [T][DP]
+    double* tabDO = reinterpret_cast<double*>(bvec + (size_t)T * DP);   // [T][7]
+    real* acc = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]  sum_s w_s eps_s, then grad
     real* wsm = acc + M;                                      // [S]
     real* part = wsm + S;                                     // [4*BS] partial sums of pass 2
     real* red = part + 4 * BS;                                // [32]
@@ -72,12 +73,17 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     const int tid = threadIdx.x;
     const uint32_t pgid = A.particle_gid0 + (uint32_t)bp;
 
-    for (int k = tid; k < T * 7; k += BS) {
-        const double* row = A.tab + (size_t)(k / 7) * SGPMP_TABLE_STRIDE;
-        tabGH[k] = (real)row[k % 7];
-        tabDO[k] = row[SGPMP_TAB_D11 + (k % 7)];
+    for (int k = tid; k < T * 8; k += BS) {
+        const int t = k >> 3, c = k & 7;
+        const double* row = A.tab + (size_t)t * SGPMP_TABLE_STRIDE;
+        tabGH[k] = c < 7 ? (real)row[c] : (real)0;
+        if (c < 7) tabDO[t * 7 + c] = row[SGPMP_TAB_D11 + c];
     }
-    for (int k = tid; k < M; k += BS) mu[k] = A.means[(size_t)bp * M + k];
+    for (int k = tid; k < T * DP; k += BS) {
+        const int t = k / DP, j = k - t * DP;
+        mu[k] = j < d ? A.means[(size_t)bp * M + t * d + j] : (real)0;
+        bvec[k] = 0;
+    }
     stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = bvec; sm.sph = sph;
@@ -94,10 +100,10 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         // ---- b = Sigma^-1 mu (fp64 accumulate) ---------------------------------------------------------
         for (int k = tid; k < T * N; k += BS) {
             const int t = k / N, i = k - t * N;
-            precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * d + i], &bvec[t * d + N + i]);
+            precision_times_row<real, DP>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
         }
         if (last && A.means_pre)
-            for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[k];
+            for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[(k / d) * DP + (k % d)];
         __syncthreads();
 
         // ---- pass 1: sample + cost, one thread per trajectory sample -----------------------------------
@@ -124,17 +130,21 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < d; ++j) e[j] = en[j];
                 }
-                const real* r = tabGH + t * 7;
+                real r[8], m[DP];
+                load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
+                load4(tabGH + t * 8 + 4, r[4], r[5], r[6], r[7]);
+#pragma unroll
+                for (int k = 0; k < DP / 4; ++k) load4(mu + t * DP + 4 * k, m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
                 real x[d];
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     const real np_ = r[0] * e[i] - (r[3] * yp[i] + r[4] * yv[i]);
                     const real nv_ = r[1] * e[i] + r[2] * e[N + i] - (r[5] * yp[i] + r[6] * yv[i]);
                     yp[i] = np_; yv[i] = nv_;
-                    x[i] = mu[t * d + i] + np_;
-                    x[N + i] = mu[t * d + N + i] + nv_;
+                    x[i] = m[i] + np_;
+                    x[N + i] = m[N + i] + nv_;
                 }
-                tc.step(P, sm, t, T, x);
+                tc.step(P, sm, t, T, x, bvec + t * DP);
                 if (emit) {
 #pragma unroll
                     for (int j = 0; j < d; ++j) A.samples[((size_t)bp * M + (size_t)t * d + j) * S + s] = x[j];
@@ -235,29 +245,29 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             const int i = tid;
             real gp_ = 0, gv_ = 0;
             for (int t = 0; t < T; ++t) {
-                const real* r = tabGH + t * 7;
+                const real* r = tabGH + t * 8;
                 const real ep = acc[t * d + i], ev = acc[t * d + N + i];
                 const real np_ = r[0] * ep - (r[3] * gp_ + r[4] * gv_);
                 const real nv_ = r[1] * ep + r[2] * ev - (r[5] * gp_ + r[6] * gv_);
                 gp_ = np_; gv_ = nv_;
                 acc[t * d + i] = gp_;
                 acc[t * d + N + i] = gv_;
-                mu[t * d + i] += A.step * gp_;
-                mu[t * d + N + i] += A.step * gv_;
+                mu[t * DP + i] += A.step * gp_;
+                mu[t * DP + N + i] += A.step * gv_;
             }
         }
         __syncthreads();
         if (last && A.grad)
             for (int k = tid; k < M; k += BS) A.grad[(size_t)bp * M + k] = acc[k];
     }
-    for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[k];
+    for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[(k / d) * DP + (k % d)];
 }
 
 template <typename real, int N, int BS, int CHAIN>
 static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
-    const int d = 2 * N, M = sh.T * d;
+    const int d = 2 * N, M = sh.T * d, DP = (d + 3) & ~3;
     const size_t smem = (size_t)sh.T * 7 * sizeof(double) +
-                        ((size_t)sh.T * 7 + 3 * (size_t)M + sh.S + 4 * BS + 32 + 2 * d + SPH_SMEM) * sizeof(real);
+                        ((size_t)sh.T * (8 + 2 * DP) + (size_t)M + sh.S + 4 * BS + 32 + 2 * d + SPH_SMEM) * sizeof(real);
     if (smem > 227 * 1024) {
         set_error("sgpmp_iterate: T=%d, S=%d need %zu bytes of shared memory (> 227 KiB)", sh.T, sh.S, smem);
         return SGPMP_ERR_UNSUPPORTED;
