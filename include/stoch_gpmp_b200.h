@@ -65,11 +65,11 @@ enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_
 
 /* Problem-batch shape.  problem_gid0 is the GLOBAL index of problem 0 of this shard: the Philox
  * counters are keyed by global problem/particle ids so that results do not depend on how the batch is
- * sharded over GPUs. */
+ * sharded over GPUs; sample_gid0 does the same for a particle's samples in split-particle mode. */
 typedef struct sgpmp_shape {
     int32_t B, G, K, S, T, n_dof;
     int32_t dtype;
-    int32_t reserved;
+    int32_t sample_gid0;   /* global index of sample 0 of this rank's slice (split-particle mode), else 0 */
     int64_t problem_gid0;
 } sgpmp_shape_t;
 

@@ -19,7 +19,7 @@ ABI_VERSION = 1
 
 class Shape(C.Structure):
     _fields_ = [("B", C.c_int32), ("G", C.c_int32), ("K", C.c_int32), ("S", C.c_int32), ("T", C.c_int32),
-                ("n_dof", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32), ("problem_gid0", C.c_int64)]
+                ("n_dof", C.c_int32), ("dtype", C.c_int32), ("sample_gid0", C.c_int32), ("problem_gid0", C.c_int64)]
 
 
 class CostDesc(C.Structure):

@@ -34,7 +34,7 @@ namespace sgpmp {
 template <typename real>
 struct IterArgs {
     int G, K, S, T, n_iters;
-    uint32_t particle_gid0;
+    uint32_t particle_gid0, sample_gid0;
     real step;
     RngKey key;            // key.draw = draw index of iteration 0
     const double* tab;
@@ -125,7 +125,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                     for (int j = 0; j < d; ++j) e[j] = eps[((size_t)t * d + j) * S + s];
                 } else if ((t & 1) == 0) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, s, pgid, e[i], e[N + i], en[i], en[N + i]);
+                    for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s, pgid, e[i], e[N + i], en[i], en[N + i]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < d; ++j) e[j] = en[j];
@@ -213,7 +213,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                         const real w = wsm[s];
                         if (w == (real)0) continue;
                         real p0, v0, p1, v1;
-                        normal4<real>(key, tp, i, s, pgid, p0, v0, p1, v1);
+                        normal4<real>(key, tp, i, A.sample_gid0 + (uint32_t)s, pgid, p0, v0, p1, v1);
                         a0 += w * p0; a1 += w * v0; a2 += w * p1; a3 += w * v1;
                     }
                 }
@@ -297,6 +297,7 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     IterArgs<real> A;
     A.G = sh.G; A.K = sh.K; A.S = sh.S; A.T = sh.T; A.n_iters = n_iters;
     A.particle_gid0 = (uint32_t)(sh.problem_gid0 * sh.G * sh.K);
+    A.sample_gid0 = (uint32_t)sh.sample_gid0;
     A.step = (real)step;
     A.key = RngKey{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw0};
     A.tab = tables;

@@ -14,7 +14,7 @@ namespace sgpmp {
 
 template <typename real>
 __global__ void __launch_bounds__(256)
-sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, const double* __restrict__ tab,
+sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
               const real* __restrict__ means, const real* __restrict__ eps_in, RngKey key,
               real* __restrict__ samples, real* __restrict__ eps_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,7 +47,7 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, const double* 
                 }
             }
         } else {
-            normal4<real>(key, tp, i, s, pgid, e[0], e[1], e[2], e[3]);
+            normal4<real>(key, tp, i, sample_gid0 + (uint32_t)s, pgid, e[0], e[1], e[2], e[3]);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -79,7 +79,7 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
         cudaFuncSetAttribute(sample_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
-    sample_kernel<real><<<grid, bs, smem, st>>>(NP, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NP, tables,
+    sample_kernel<real><<<grid, bs, smem, st>>>(NP, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NP, (uint32_t)sh.sample_gid0, tables,
                                                 (const real*)means, (const real*)eps_in, key, (real*)samples,
                                                 (real*)eps_out);
     SGPMP_CHECK_LAUNCH("sgpmp_sample");

@@ -34,10 +34,10 @@ def _req(t, name, dtype=None, shape=None):
     return t
 
 
-def make_shape(B, G, K, S, T, n_dof, dtype, problem_gid0=0):
+def make_shape(B, G, K, S, T, n_dof, dtype, problem_gid0=0, sample_gid0=0):
     if dtype not in _DT:
         raise TypeError("dtype must be torch.float32 or torch.float64, got %s" % dtype)
-    return _lib.Shape(B=B, G=G, K=K, S=S, T=T, n_dof=n_dof, dtype=_DT[dtype], reserved=0, problem_gid0=problem_gid0)
+    return _lib.Shape(B=B, G=G, K=K, S=S, T=T, n_dof=n_dof, dtype=_DT[dtype], sample_gid0=sample_gid0, problem_gid0=problem_gid0)
 
 
 def prior_factor(D, O):
