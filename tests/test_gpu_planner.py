@@ -200,3 +200,101 @@ def test_error_behaviour(cuda, lib):
         StochGPMP(1, 4, 8, 1, dt=0.1, n_dof=5, start_state=torch.zeros(10, **ta), multi_goal_states=torch.zeros(1, 10, **ta),
                   cost=None, sigma_start_init=1., sigma_start_sample=1., sigma_goal_init=1., sigma_goal_sample=1.,
                   sigma_gp_init=1., sigma_gp_sample=1., tensor_args=ta)
+
+
+# ------------------------------------------------------------------------------- BASELINE.json shapes
+def _oracle_check_inkernel(pl, spec, obs, n_iters, tol_cost, tol_mean):
+    """Run `n_iters` optimize() iterations with the in-kernel Philox stream and check each against the numpy
+    oracle fed the oracle-side restatement of that stream (costs vs oracle; update on the kernel's own costs)."""
+    from oracle import philox as OPH
+    from oracle import update as U
+    NP, S, T, n = spec['G'] * spec['K'], spec['S'], spec['T'], spec['n_dof']
+    for _ in range(n_iters):
+        mu = pl.particle_means.cpu().numpy().astype(np.float64)
+        draw = pl._draw
+        out = pl.optimize(**obs)
+        eps = OPH.normals(pl.seed, draw, np.arange(NP), S, T, n)
+        r = OP.iterate(spec, mu, eps)
+        costs = out[4].cpu().numpy().astype(np.float64)
+        assert rel(out[2].cpu().numpy(), r['samples'][..., :n]) < tol_cost
+        assert rel(costs, r['costs']) < tol_cost
+        mp, grad, w = U.update(mu, r['samples'], costs, spec['temperature'], spec['step_size'])
+        assert np.abs(pl._weights.cpu().numpy().reshape(NP, S) - w).max() < 10 * tol_cost
+        assert rel(pl.particle_means.cpu().numpy(), mp) < tol_mean
+
+
+def test_c1_planar_as_shipped_shape_fp64(cuda):
+    """BASELINE configs[0]: examples/planar_environment.py as shipped — G=3, K=5, S=128, T=64, n=2, fp64, the
+    generator's 200x200 map (seed 0), shipped sigmas — three iterations against the oracle."""
+    import random
+    from oracle.scenarios import PLANAR_COST, PLANAR_GOALS, PLANAR_SIGMAS
+    from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
+    from stoch_gpmp_b200.envs.map_generator import generate_obstacle_map
+    from stoch_gpmp_b200.planner import StochGPMP
+    n, T, K, S, dt = 2, 64, 5, 128, 0.02
+    ta = dict(device=cuda, dtype=torch.float64)
+    start = torch.tensor([-9., -9., 0., 0.], **ta)
+    goals = torch.tensor(PLANAR_GOALS, **ta)
+    random.seed(0)
+    np.random.seed(0)
+    om = generate_obstacle_map(map_dim=[20, 20], obst_list=[], cell_size=0.1, random_gen=True, num_obst=15,
+                               rand_limits=[[-7.5, 7.5], [-7.5, 7.5]], rand_rect_shape=[2, 2], tensor_args=ta)[0]
+    cost = CostComposite(n, T, [
+        CostGP(n, T, start, dt, dict(sigma_start=PLANAR_COST['sigma_start'], sigma_gp=PLANAR_COST['sigma_gp']), ta),
+        CostGoalPrior(n, T, multi_goal_states=goals, num_particles_per_goal=K, num_samples=S,
+                      sigma_goal_prior=PLANAR_COST['sigma_goal_prior'], tensor_args=ta),
+        CostCollision(n, T, field=om, sigma_coll=PLANAR_COST['sigma_coll'])])
+    pl = StochGPMP(num_particles_per_goal=K, num_samples=S, traj_len=T, opt_iters=1, dt=dt, n_dof=n, temperature=1.,
+                   start_state=start, multi_goal_states=goals, cost=cost, step_size=0.5, seed=0, tensor_args=ta, **PLANAR_SIGMAS)
+    spec = dict(n_dof=n, T=T, dt=dt, G=3, K=K, S=S, temperature=1., step_size=0.5, start=start.cpu().numpy(),
+                goals=goals.cpu().numpy(), map=om.map, map_cell_size=0.1, map_origin=(om.origin_xi, om.origin_yi),
+                cost_sigma_start=PLANAR_COST['sigma_start'], cost_sigma_gp=PLANAR_COST['sigma_gp'],
+                sigma_goal_prior=PLANAR_COST['sigma_goal_prior'], sigma_coll=PLANAR_COST['sigma_coll'], **PLANAR_SIGMAS)
+    # the initial means come from the INIT prior with the kernel's stream: check them against the oracle too
+    from oracle import philox as OPH
+    init_eps = OPH.normals(0, 0, np.arange(3), K, T, n)                                  # [G, K, T, d]
+    m0 = OP.initial_means(spec, np.transpose(init_eps, (1, 0, 2, 3)).reshape(K, 3, T * 2 * n))
+    assert rel(pl.particle_means.cpu().numpy(), m0) < 1e-10
+    _oracle_check_inkernel(pl, spec, {}, 3, 1e-10, 1e-10)
+
+
+def test_c3_panda_single_problem_shape_fp32(cuda):
+    """BASELINE configs[2]: Panda single problem, 4 goals x 512 samples x T=64, fp32, shipped sigmas, O=5 spheres."""
+    from oracle.scenarios import PANDA_COST, PANDA_SIGMAS, PANDA_START, panda_goals, panda_spheres
+    from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
+    from stoch_gpmp_b200.costs.fields import LinkDistanceField
+    from stoch_gpmp_b200.planner import StochGPMP
+    from stoch_gpmp_b200.robots import PandaFK
+    n, T, G, K, S, dt = 7, 64, 4, 1, 512, 0.05
+    ta = dict(device=cuda, dtype=torch.float32)
+    start, goals, spheres = np.array(PANDA_START), np.array(panda_goals(G, 0)), np.array(panda_spheres(5, 0))
+    s_t, g_t = torch.tensor(start, **ta), torch.tensor(goals, **ta)
+    cost = CostComposite(n, T, [
+        CostGP(n, T, s_t, dt, dict(sigma_start=PANDA_COST['sigma_start'], sigma_gp=PANDA_COST['sigma_gp']), ta),
+        CostGoalPrior(n, T, multi_goal_states=g_t, num_particles_per_goal=K, num_samples=S,
+                      sigma_goal_prior=PANDA_COST['sigma_goal_prior'], tensor_args=ta),
+        CostCollision(n, T, field=LinkDistanceField(tensor_args=ta), sigma_coll=PANDA_COST['sigma_coll'])], FK=PandaFK(), tensor_args=ta)
+    pl = StochGPMP(num_particles_per_goal=K, num_samples=S, traj_len=T, opt_iters=1, dt=dt, n_dof=n, step_size=0.1, temperature=1.,
+                   start_state=s_t, multi_goal_states=g_t, initial_particle_means='const_vel', cost=cost, seed=3, tensor_args=ta,
+                   **PANDA_SIGMAS)
+    spec = dict(n_dof=n, T=T, dt=dt, G=G, K=K, S=S, temperature=1., step_size=0.1, start=start, goals=goals, spheres=spheres,
+                cost_sigma_start=PANDA_COST['sigma_start'], cost_sigma_gp=PANDA_COST['sigma_gp'],
+                sigma_goal_prior=PANDA_COST['sigma_goal_prior'], sigma_coll=PANDA_COST['sigma_coll'], **PANDA_SIGMAS)
+    obs = {'obstacle_spheres': torch.tensor(spheres, **ta).unsqueeze(0)}
+    _oracle_check_inkernel(pl, spec, obs, 2, 1e-5, 1e-5)
+
+
+def test_user_supplied_initial_means(cuda):
+    """initial_particle_means as a [G,K,T,d] tensor (planner.py:202-203) and reset() with new start/goals."""
+    g = load('planar_f64')
+    spec = OP.spec_from_golden(g)
+    T, d, G, K = spec['T'], 2 * spec['n_dof'], spec['G'], spec['K']
+    pm = torch.tensor(g['it0_means_pre'].reshape(G, K, T, d), device=cuda)
+    pl = _planner(g, spec, cuda, torch.float64, initial_particle_means=pm)
+    assert np.array_equal(pl.particle_means.cpu().numpy(), g['it0_means_pre'])
+    eps = torch.tensor(to_sminor(eps_ref_to_traj(g['it0_eps'], T, d)), device=cuda)
+    out = pl.optimize(_eps=eps)
+    assert rel(out[4].cpu().numpy(), g['it0_costs']) < 1e-10
+    assert rel(pl.particle_means.cpu().numpy(), g['it0_means_post']) < 1e-10
+    with pytest.raises(AssertionError):
+        pl.reset(initial_particle_means=torch.zeros(G, K + 1, T, d, device=cuda, dtype=torch.float64))
