@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGPMP_ABI_VERSION 1
+#define SGPMP_ABI_VERSION 2
 
 enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
 
@@ -60,8 +60,9 @@ enum {
 
 #define SGPMP_MAX_FRAMES 16
 #define SGPMP_MAX_SPHERES 16
-#define SGPMP_NUM_TERMS 5
-enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_COLL = 3, SGPMP_TERM_IS = 4 };
+#define SGPMP_NUM_TERMS 6
+/* total = ((((start + gp) + goal) + self) + coll) + is */
+enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_COLL = 3, SGPMP_TERM_IS = 4, SGPMP_TERM_SELF = 5 };
 
 /* Problem-batch shape.  problem_gid0 is the GLOBAL index of problem 0 of this shard: the Philox
  * counters are keyed by global problem/particle ids so that results do not depend on how the batch is
@@ -79,6 +80,7 @@ typedef struct sgpmp_shape {
  *   CostCollision   cost_functions.py:223-261  sigma_coll + field:
  *       ObstacleMap         envs/obst_map.py:108-188     (occupancy grid lookup)
  *       LinkDistanceField   costs/fields.py:30-86 'rbf'  (FK link positions vs obstacle spheres)
+ *       LinkSelfDistanceField costs/fields.py:89-127     (FK link positions vs each other; own sigma)
  *   IS term         planner.py:233-236         temperature * x^T Sigma^-1 mu
  * FK chain = the callable the reference passes as CostComposite(FK=...) (cost_functions.py:39-52),
  * restated as a serial chain of fixed transforms + revolute z joints. */
@@ -113,6 +115,11 @@ typedef struct sgpmp_cost_desc {
     double chain_R[SGPMP_MAX_FRAMES][9];  /* fixed rotation parent->child, row-major */
     double chain_p[SGPMP_MAX_FRAMES][3];  /* fixed translation parent->child */
     int32_t chain_joint[SGPMP_MAX_FRAMES];/* joint index rotating about child z, or -1 (fixed) */
+
+    /* self-collision field (needs the FK chain): sum_{i,j} exp(-|p_i - p_j|^2 / (2 margin^2)) over all ordered
+     * pairs of link frames incl. i == j, weight 1/self_sigma_coll^2 */
+    double self_margin;              /* <= 0: absent */
+    double self_sigma_coll;
 } sgpmp_cost_desc_t;
 
 int sgpmp_abi_version(void);

@@ -12,6 +12,7 @@ Reference call sites restated (all in /root/reference/stoch_gpmp):
                        costs/factors/field_factor.py:18-32  (time steps 1..T-1 only)
   ObstacleMap.get_collisions  envs/obst_map.py:164-182
   LinkDistanceField.compute_cost ('rbf')  costs/fields.py:63-79
+  LinkSelfDistanceField.compute_cost      costs/fields.py:114-124
   importance-sampling term    planner.py:229-237   tau * x^T Sigma^-1 mu
 
 Every function takes samples x [NP, S, T, d] and returns [NP, S].
@@ -76,6 +77,21 @@ def cost_collision_spheres(x, spheres, sigma_coll, fk_fn):
     H = fk_fn(q)
     pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
     return sphere_rbf(pos, spheres).sum(-1) * (1.0 / sigma_coll ** 2)
+
+
+def self_rbf(link_pos, margin):
+    """link_pos [..., L, 3] -> [...]: sum over ALL ordered pairs (i == j included) of
+    exp(-|p_i - p_j|^2 / (2 margin^2)).  LinkSelfDistanceField.compute_cost, costs/fields.py:114-124."""
+    diff = link_pos[..., :, None, :] - link_pos[..., None, :, :]
+    return np.exp((diff * diff).sum(-1) / (-margin ** 2 * 2)).sum((-1, -2))
+
+
+def cost_self_collision(x, margin, sigma_self, fk_fn):
+    NP, S, T, d = x.shape
+    n = d // 2
+    H = fk_fn(x[:, :, 1:, :n].reshape(-1, n))
+    pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
+    return self_rbf(pos, margin).sum(-1) * (1.0 / sigma_self ** 2)
 
 
 def cost_importance(x, means, D, O, temperature):

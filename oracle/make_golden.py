@@ -33,7 +33,7 @@ def _np(t):
 
 def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_sigmas, cost_sigmas,
              temperature, step_size, iters, map_params=None, spheres=None, initial_particle_means=None,
-             sigma_coll=None, sigma_goal_prior=None, store_L=True):
+             sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None):
     ref = ref_loader.load()
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
     start_state = torch.tensor(start, **ta)
@@ -69,6 +69,13 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
         rec['map'] = obst_map.map.copy()
         rec['map_cell_size'] = map_params['cell_size']
         rec['map_origin'] = np.array([obst_map.origin_xi, obst_map.origin_yi])
+    if self_field is not None:      # (margin, sigma_self): examples/panda_environment.py:67,88 — listed BEFORE the obstacle cost
+        from stoch_gpmp.costs.fields import LinkSelfDistanceField
+        FK = ofk.fk_all_links_torch()
+        cost_list.append(ref.CostCollision(n_dof, T, field=LinkSelfDistanceField(margin=self_field[0], tensor_args=ta),
+                                           sigma_coll=self_field[1]))
+        term_names.append('self')
+        rec['self_margin'], rec['sigma_self'] = self_field
     if spheres is not None:
         FK = ofk.fk_all_links_torch()
         field = ref.LinkDistanceField(tensor_args=ta)
@@ -232,6 +239,20 @@ def main():
                  start=PANDA_START, goals=panda_goals(2, 0), planner_sigmas=PANDA_SIGMAS,
                  cost_sigmas=dict(sigma_start=0.0001, sigma_gp=0.0007), sigma_coll=0.01, sigma_goal_prior=20.,
                  temperature=1., step_size=0.1, iters=2, spheres=panda_spheres(3, 0))
+    # shipped Panda cost list minus the EE-goal term: + LinkSelfDistanceField(margin=0.03), sigma_self=0.01
+    # (examples/panda_environment.py:67,78,88-90), fp32 and fp64; a soft fp64 variant with live weights
+    for nm, dt_ in (('panda_self_f32', torch.float32), ('panda_self_f64', torch.float64)):
+        run_case(nm, n_dof=7, T=16, dt=0.05, G=2, K=2, S=8, dtype=dt_, seed=7,
+                 start=PANDA_START, goals=panda_goals(2, 2), planner_sigmas=PANDA_SIGMAS,
+                 cost_sigmas=dict(sigma_start=0.0001, sigma_gp=0.0007), sigma_coll=0.01, sigma_goal_prior=20.,
+                 temperature=1., step_size=0.1, iters=2, spheres=panda_spheres(5, 2), self_field=(0.03, 0.01))
+    run_case('panda_self_soft_f64', n_dof=7, T=16, dt=0.05, G=2, K=1, S=16, dtype=torch.float64, seed=8,
+             start=PANDA_START, goals=panda_goals(2, 3),
+             planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.8,
+                                 sigma_start_sample=4.0, sigma_goal_sample=4.0, sigma_gp_sample=0.5),
+             initial_particle_means='const_vel',
+             cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
+             temperature=200., step_size=0.5, iters=2, spheres=None, self_field=(0.15, 0.1))
     # Panda with soft sigmas / temperature (non-degenerate weights).  fp32 only constructs for mild
     # conditioning (torch's fp32 Cholesky of the precision fails otherwise — SURVEY §6/§7), so the
     # softer variant is fp64.

@@ -14,6 +14,7 @@ Reference: StochGPMP.reset / sample_and_eval / _get_costs / _update_distribution
   sigma_coll or None, and ONE of
      map [H,W], map_cell_size, map_origin (xi, yi)        ObstacleMap (envs/obst_map.py:112-147)
      spheres [O,4]                                        LinkDistanceField 'rbf' (costs/fields.py:63-79)
+  self_margin, sigma_self (optional)                      LinkSelfDistanceField (costs/fields.py:89-127)
 """
 import numpy as np
 
@@ -42,6 +43,9 @@ def spec_from_golden(g):
         s['map_origin'] = (int(g['map_origin'][0]), int(g['map_origin'][1]))
     if 'spheres' in g.files:
         s['spheres'] = g['spheres']
+    if 'self_margin' in g.files:
+        s['self_margin'] = float(g['self_margin'])
+        s['sigma_self'] = float(g['sigma_self'])
     return s
 
 
@@ -85,6 +89,9 @@ def eval_costs(spec, samples, means, D, O, dtype=np.float64):
     if spec.get('goals') is not None and spec.get('sigma_goal_prior') is not None:
         terms['goal'] = C.cost_goal_prior(x, spec['goals'].astype(dtype), spec['K'], spec['sigma_goal_prior'])
         total = total + terms['goal']
+    if spec.get('self_margin') is not None:
+        terms['self'] = C.cost_self_collision(x, spec['self_margin'], spec['sigma_self'], lambda q: FK.fk_all_links(q))
+        total = total + terms['self']
     if spec.get('sigma_coll') is not None and 'map' in spec:
         terms['coll'] = C.cost_collision_map(x, spec['map'], spec['map_cell_size'], spec['map_origin'][0],
                                              spec['map_origin'][1], spec['sigma_coll'])

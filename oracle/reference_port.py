@@ -124,6 +124,11 @@ class ReferencePort:
                 eg = self.goals[i] - xg[i, :, [-1]]
                 gc[i] += (eg @ self.K_goal.unsqueeze(0) @ eg.transpose(1, 2)).squeeze()
             costs = costs + gc.flatten()
+        # CostCollision(LinkSelfDistanceField)   costs/fields.py:114-124
+        if s.get('self_margin') is not None:
+            lt = x_trajs[:, 1:T][..., :3, -1]
+            selfc = torch.exp(torch.square(lt.unsqueeze(-2) - lt.unsqueeze(-3)).sum(-1) / (-s['self_margin'] ** 2 * 2)).sum((-1, -2))
+            costs = costs + (1. / s['sigma_self'] ** 2) * selfc.sum(1)
         # CostCollision
         if s.get('sigma_coll') is not None and self.map is not None:
             X = trajs[:, 1:T, :n].reshape(-1, n)

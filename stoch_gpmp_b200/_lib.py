@@ -12,9 +12,9 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 TABLE_STRIDE = 16
 MAX_FRAMES = 16
 MAX_SPHERES = 16
-NUM_TERMS = 5
-TERM_NAMES = ("start", "gp", "goal", "coll", "is")
-ABI_VERSION = 1
+NUM_TERMS = 6
+TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self")
+ABI_VERSION = 2
 
 
 class Shape(C.Structure):
@@ -36,6 +36,7 @@ class CostDesc(C.Structure):
         ("n_frames", C.c_int32), ("include_base", C.c_int32),
         ("chain_R", (C.c_double * 9) * MAX_FRAMES), ("chain_p", (C.c_double * 3) * MAX_FRAMES),
         ("chain_joint", C.c_int32 * MAX_FRAMES),
+        ("self_margin", C.c_double), ("self_sigma_coll", C.c_double),
     ]
 
 

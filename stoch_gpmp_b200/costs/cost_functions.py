@@ -16,7 +16,7 @@ from .. import _lib
 from .. import ops
 from ..envs.occupancy import ObstacleMap
 from ..robots.serial_chain import SerialChainFK
-from .fields import LinkDistanceField
+from .fields import LinkDistanceField, LinkSelfDistanceField
 
 
 class Cost:
@@ -69,8 +69,11 @@ class CostGoalPrior(Cost):
 
 class CostCollision(Cost):
     """Obstacle factor over time steps 1..T-1.  field: ObstacleMap (or a list of them, one per problem of a
-    batch) or LinkDistanceField('rbf'); None disables the term as in the reference."""
-    _term = 'coll'
+    batch), LinkDistanceField('rbf') or LinkSelfDistanceField; None disables the term as in the reference."""
+
+    @property
+    def _term(self):
+        return 'self' if isinstance(self.field, LinkSelfDistanceField) else 'coll'
 
     def __init__(self, n_dof, traj_len, field=None, sigma_coll=None, tensor_args=None):
         super().__init__(n_dof, traj_len)
@@ -94,7 +97,7 @@ class LoweredCost:
 
     def __init__(self, composite, B, G, device, dtype):
         self.B, self.G, self.device, self.dtype = B, G, device, dtype
-        gp = goal = coll = None
+        gp = goal = coll = selfc = None
         for c in composite.cost_list:
             if isinstance(c, CostGP):
                 if gp is not None:
@@ -107,8 +110,13 @@ class LoweredCost:
             elif isinstance(c, CostCollision):
                 if c.field is None:
                     continue                      # the reference returns 0 for a field-less collision cost
+                if isinstance(c.field, LinkSelfDistanceField):
+                    if selfc is not None:
+                        raise NotImplementedError("more than one self-collision field in cost_list")
+                    selfc = c
+                    continue
                 if coll is not None:
-                    raise NotImplementedError("more than one collision field in cost_list (SURVEY §8f rank 1)")
+                    raise NotImplementedError("more than one obstacle field in cost_list")
                 coll = c
             else:
                 raise NotImplementedError("cost object %s cannot be lowered to the CUDA path (no CPU fallback)"
@@ -130,6 +138,11 @@ class LoweredCost:
         self.map_meta = None
         self.sphere_sigma = None
         self.fk = None
+        self.self_margin = self.self_sigma = None
+        if selfc is not None:
+            selfc.field.check_lowerable()
+            self._need_fk(composite, n)
+            self.self_margin, self.self_sigma = float(selfc.field.margin), float(selfc.sigma_coll)
         if coll is not None:
             fields = coll.field if isinstance(coll.field, (list, tuple)) else [coll.field]
             if all(isinstance(f, ObstacleMap) for f in fields):
@@ -151,20 +164,34 @@ class LoweredCost:
                                      inv_cell=1.0 / f0.cell_size, sigma=float(coll.sigma_coll))
             elif len(fields) == 1 and isinstance(fields[0], LinkDistanceField):
                 fields[0].check_lowerable()
-                if not isinstance(composite.FK, SerialChainFK):
-                    raise NotImplementedError(
-                        "LinkDistanceField needs CostComposite(FK=<stoch_gpmp_b200.robots.SerialChainFK>), e.g. PandaFK(); "
-                        "arbitrary FK callables cannot be lowered to the CUDA kernel")
-                self.fk = composite.FK
-                if self.fk.n_dofs != n:
-                    raise ValueError("FK chain has %d joints but n_dof=%d" % (self.fk.n_dofs, n))
-                if len(self.fk.joint) > _lib.MAX_FRAMES:
-                    raise NotImplementedError("FK chain longer than %d frames" % _lib.MAX_FRAMES)
+                self._need_fk(composite, n)
                 self.sphere_sigma = float(coll.sigma_coll)
             else:
                 raise NotImplementedError("collision field %s cannot be lowered to the CUDA path"
                                           % type(fields[0]).__name__)
         self._spheres = None
+
+    def _need_fk(self, composite, n):
+        if not isinstance(composite.FK, SerialChainFK):
+            raise NotImplementedError(
+                "link distance fields need CostComposite(FK=<stoch_gpmp_b200.robots.SerialChainFK>), e.g. PandaFK(); "
+                "arbitrary FK callables cannot be lowered to the CUDA kernel")
+        self.fk = composite.FK
+        if self.fk.n_dofs != n:
+            raise ValueError("FK chain has %d joints but n_dof=%d" % (self.fk.n_dofs, n))
+        if len(self.fk.joint) > _lib.MAX_FRAMES:
+            raise NotImplementedError("FK chain longer than %d frames" % _lib.MAX_FRAMES)
+
+    def _fill_chain(self, d):
+        fk = self.fk
+        d.n_frames = len(fk.joint)
+        d.include_base = 1 if fk.include_base else 0
+        for f in range(len(fk.joint)):
+            for k in range(9):
+                d.chain_R[f][k] = fk.R[f][k]
+            for k in range(3):
+                d.chain_p[f][k] = fk.xyz[f][k]
+            d.chain_joint[f] = fk.joint[f]
 
     def desc(self, temperature, obstacle_spheres=None):
         """Fill an sgpmp_cost_desc_t (keeps the tensors it points to alive on self)."""
@@ -181,32 +208,24 @@ class LoweredCost:
             d.n_maps, d.map_h, d.map_w = self.map.shape[0], m['h'], m['w']
             d.origin_xi, d.origin_yi = m['oxi'], m['oyi']
             d.map_inv_cell, d.map_sigma_coll = m['inv_cell'], m['sigma']
-        if self.fk is not None:
-            if obstacle_spheres is None:
-                # reference: LinkDistanceField.compute_cost returns 0 without spheres (fields.py:64-65)
-                d.spheres = None
-            else:
-                sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
-                if sp.dim() == 2:
-                    sp = sp.unsqueeze(0)
-                if sp.shape[0] not in (1, self.B) or sp.shape[-1] != 4:
-                    raise ValueError("obstacle_spheres must be [1,O,4] or [B,O,4], got %s" % (tuple(sp.shape),))
-                if sp.shape[1] > _lib.MAX_SPHERES:
-                    raise NotImplementedError("more than %d obstacle spheres" % _lib.MAX_SPHERES)
-                self._spheres = sp.contiguous()
-                d.spheres = self._spheres.data_ptr()
-                d.n_spheres = sp.shape[1]
-                d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
-                d.sphere_sigma_coll = self.sphere_sigma
-                fk = self.fk
-                d.n_frames = len(fk.joint)
-                d.include_base = 1 if fk.include_base else 0
-                for f in range(len(fk.joint)):
-                    for k in range(9):
-                        d.chain_R[f][k] = fk.R[f][k]
-                    for k in range(3):
-                        d.chain_p[f][k] = fk.xyz[f][k]
-                    d.chain_joint[f] = fk.joint[f]
+        if self.self_margin is not None:
+            d.self_margin, d.self_sigma_coll = self.self_margin, self.self_sigma
+            self._fill_chain(d)
+        if self.sphere_sigma is not None and obstacle_spheres is not None:
+            # (without spheres the reference's LinkDistanceField.compute_cost returns 0, fields.py:64-65)
+            sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
+            if sp.dim() == 2:
+                sp = sp.unsqueeze(0)
+            if sp.shape[0] not in (1, self.B) or sp.shape[-1] != 4:
+                raise ValueError("obstacle_spheres must be [1,O,4] or [B,O,4], got %s" % (tuple(sp.shape),))
+            if sp.shape[1] > _lib.MAX_SPHERES:
+                raise NotImplementedError("more than %d obstacle spheres" % _lib.MAX_SPHERES)
+            self._spheres = sp.contiguous()
+            d.spheres = self._spheres.data_ptr()
+            d.n_spheres = sp.shape[1]
+            d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
+            d.sphere_sigma_coll = self.sphere_sigma
+            self._fill_chain(d)
         return d
 
 

@@ -1,6 +1,7 @@
 """Distance fields (parameter carriers).  Mirrors stoch_gpmp/costs/fields.py for the variants on the
-StochGPMP hot path: LinkDistanceField with field_type='rbf' and no link interpolation
-(costs/fields.py:30-79).  The arithmetic runs in csrc/sgpmp_cost.cuh::link_sphere_rbf."""
+StochGPMP hot path: LinkDistanceField with field_type='rbf' (costs/fields.py:30-79) and
+LinkSelfDistanceField (costs/fields.py:89-127), both without link interpolation.  The arithmetic runs in
+csrc/sgpmp_cost.cuh::link_fields."""
 
 
 class DistanceField:
@@ -30,8 +31,18 @@ class LinkDistanceField(DistanceField):
 
 
 class LinkSelfDistanceField(DistanceField):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("LinkSelfDistanceField is outside the round-1 hot path (SURVEY §8f rank 1); no CPU fallback")
+    """sum over ALL ordered pairs of link frames (i == j included) of exp(-|p_i - p_j|^2 / (2 margin^2))
+    (costs/fields.py:89-127).  Arithmetic: csrc/sgpmp_cost.cuh::link_fields."""
+
+    def __init__(self, margin=0.03, num_interpolate=0, link_interpolate_range=(5, 7), **kwargs):
+        super().__init__(**kwargs)
+        self.margin = margin
+        self.num_interpolate = num_interpolate
+        self.link_interpolate_range = list(link_interpolate_range)
+
+    def check_lowerable(self):
+        if self.num_interpolate:
+            raise NotImplementedError("LinkSelfDistanceField(num_interpolate>0) is not lowered yet (SURVEY §8f rank 1)")
 
 
 class EESE3DistanceField(DistanceField):

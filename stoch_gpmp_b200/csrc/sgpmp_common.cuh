@@ -57,7 +57,8 @@ struct CostParams {
     real R[SGPMP_MAX_FRAMES][9];
     real p[SGPMP_MAX_FRAMES][3];
     int32_t joint[SGPMP_MAX_FRAMES];
-    int32_t has_goal, has_map, has_spheres;
+    int32_t has_goal, has_map, has_spheres, has_self;
+    real self_k, self_w_coll;   // self_k = -0.5/margin^2 (* log2 e in fp32)
 };
 
 template <typename real>

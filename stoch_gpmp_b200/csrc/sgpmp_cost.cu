@@ -32,10 +32,6 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
     o.inv_sig_goal2 = o.has_goal ? (real)(1.0 / (d.sigma_goal_prior * d.sigma_goal_prior)) : (real)0;
     o.has_map = d.occ_map != nullptr;
     o.has_spheres = d.spheres != nullptr && d.n_spheres > 0;
-    if (o.has_map && o.has_spheres) {
-        set_error("cost desc: one collision field per problem batch (map or spheres), got both");
-        return SGPMP_ERR_UNSUPPORTED;
-    }
     if (o.has_map) {
         if (d.map_h <= 0 || d.map_w <= 0 || d.n_maps <= 0 || !(d.map_sigma_coll > 0)) {
             set_error("cost desc: bad occupancy-map parameters");
@@ -56,11 +52,14 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
         o.map_origin_y = (real)d.origin_yi;
         o.map_w_coll = (real)(1.0 / (d.map_sigma_coll * d.map_sigma_coll));
     }
-    if (o.has_spheres) {
-        if (d.n_spheres > SGPMP_MAX_SPHERES || !(d.sphere_sigma_coll > 0)) {
-            set_error("cost desc: n_spheres must be <= %d and sigma_coll > 0", SGPMP_MAX_SPHERES);
-            return SGPMP_ERR_INVALID_ARG;
-        }
+    o.has_self = d.self_margin > 0;
+    if (o.has_self && !(d.self_sigma_coll > 0)) { set_error("cost desc: self_sigma_coll must be > 0"); return SGPMP_ERR_INVALID_ARG; }
+    if (o.has_spheres && (d.n_spheres > SGPMP_MAX_SPHERES || !(d.sphere_sigma_coll > 0))) {
+        set_error("cost desc: n_spheres must be <= %d and sigma_coll > 0", SGPMP_MAX_SPHERES);
+        return SGPMP_ERR_INVALID_ARG;
+    }
+    if (o.has_spheres || o.has_self) {
+        if (o.has_map) { set_error("cost desc: link fields and an occupancy map cannot be combined"); return SGPMP_ERR_UNSUPPORTED; }
         if (d.n_frames < sh.n_dof || d.n_frames > SGPMP_MAX_FRAMES) {
             set_error("cost desc: FK chain needs n_dof <= n_frames <= %d", SGPMP_MAX_FRAMES);
             return SGPMP_ERR_INVALID_ARG;
@@ -73,10 +72,6 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
                 return SGPMP_ERR_UNSUPPORTED;
             }
         }
-        o.spheres = (const real*)d.spheres;
-        o.n_spheres = d.n_spheres;
-        o.spheres_per_problem = d.spheres_per_problem;
-        o.sphere_w_coll = (real)(1.0 / (d.sphere_sigma_coll * d.sphere_sigma_coll));
         o.n_frames = d.n_frames;
         o.include_base = d.include_base;
         for (int f = 0; f < d.n_frames; ++f) {
@@ -84,6 +79,16 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
             for (int k = 0; k < 3; ++k) o.p[f][k] = (real)d.chain_p[f][k];
             o.joint[f] = d.chain_joint[f];
         }
+    }
+    if (o.has_spheres) {
+        o.spheres = (const real*)d.spheres;
+        o.n_spheres = d.n_spheres;
+        o.spheres_per_problem = d.spheres_per_problem;
+        o.sphere_w_coll = (real)(1.0 / (d.sphere_sigma_coll * d.sphere_sigma_coll));
+    }
+    if (o.has_self) {
+        o.self_k = (real)((sizeof(real) == 4 ? -0.5 * 1.4426950408889634 : -0.5) / (d.self_margin * d.self_margin));
+        o.self_w_coll = (real)(1.0 / (d.self_sigma_coll * d.self_sigma_coll));
     }
     return SGPMP_OK;
 }
@@ -126,6 +131,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = means ? bvec : nullptr; sm.sph = sph;
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
+    sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
 
     TrajCost<real, N, CHAIN> tc;
@@ -146,6 +152,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
         terms[SGPMP_TERM_GOAL * term_stride + o] = tc.c_goal;
         terms[SGPMP_TERM_COLL * term_stride + o] = tc.c_coll;
         terms[SGPMP_TERM_IS * term_stride + o] = tc.c_is;
+        terms[SGPMP_TERM_SELF * term_stride + o] = tc.c_self;
     }
 }
 
@@ -220,8 +227,9 @@ static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
     if constexpr (sizeof(real) == 4) {
-        if (P.has_spheres && chain_is_panda_structure(desc, sh.n_dof))
-            return launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
+        if ((P.has_spheres || P.has_self) && chain_is_panda_structure(desc, sh.n_dof))
+            return P.has_self ? launch_cost_n<real, 7, 2>(sh, P, tables, samples, means, costs, terms, st)
+                              : launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
     }
     switch (sh.n_dof) {
 #define SGPMP_DOF_CASE(N) case N: return launch_cost_n<real, N, 0>(sh, P, tables, samples, means, costs, terms, st);

@@ -38,6 +38,7 @@ struct CostSmem {
                          //          a = -2 k c, b = k |c|^2  so that  k |p - c|^2 = k |p|^2 + a.p + b
     const real* map;     // occupancy map of this problem (global memory)
     real coll_const;     // RBF sum of the link frames whose position does not depend on q (structured chains)
+    real self_const;     // q-independent part of the self-collision sum (structured chains)
 };
 
 constexpr int SPH_STRIDE = 8;
@@ -106,7 +107,7 @@ __device__ __forceinline__ void fk_visit_links(const CostParams<real>& P, const 
 
 // ---- structured chains ------------------------------------------------------------------------------
 // CHAIN = 0: generic serial arm (fk_visit_links, runtime constants).
-// CHAIN = 1: "Panda structure" (7 joints): fixed rotations are identity / Rx(+-90 deg) / about-z, and most
+// CHAIN = 1 (spheres only) / 2 (+ self-collision code): "Panda structure" (7 joints): fixed rotations are identity / Rx(+-90 deg) / about-z, and most
 // translation components are zero (panda_arm_no_gripper.urdf).  The STRUCTURE is compile-time — Rx(+-90)
 // becomes a signed relabelling of columns, zero translation components vanish — while the translation VALUES
 // still come from the descriptor.  The host selects it only when the descriptor matches this structure
@@ -174,45 +175,97 @@ __device__ __forceinline__ void fk_panda_origins(const CostParams<real>& P, cons
 
 template <typename real, int N, int CHAIN = 0>
 struct TrajCost {
-    real c_start, c_gp, c_goal, c_coll, c_is;
+    real c_start, c_gp, c_goal, c_coll, c_is, c_self;
     real xp[2 * N];   // previous state
 
-    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = 0; }
+    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = 0; }
 
-    // sum_l sum_o exp(-0.5 |p_l - c_o|^2 / r_o^2) over the link frames of configuration q
-    __device__ __forceinline__ real link_sphere_rbf(const CostParams<real>& P, const CostSmem<real>& sm,
-                                                    const real* q) const {
-        real acc = 0;
+    // Link fields of configuration q (one FK evaluation shared by both):
+    //   spheres  sum_l sum_o exp(-0.5 |p_l - c_o|^2 / r_o^2)            LinkDistanceField 'rbf'   costs/fields.py:63-79
+    //   self     sum_{i,j} exp(-|p_i - p_j|^2 / (2 margin^2)), all ordered pairs incl. i == j
+    //                                                                    LinkSelfDistanceField     costs/fields.py:114-124
+    __device__ __forceinline__ void link_fields(const CostParams<real>& P, const CostSmem<real>& sm, const real* q) {
         const int O = P.n_spheres;
-        if constexpr (CHAIN == 1) {
+        if constexpr (CHAIN >= 1) {
             static_assert(N == 7, "Panda structure has 7 joints");
             real X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS], PP[PANDA_EVAL_LINKS];
             fk_panda_origins<real>(P, q, X, Y, Z);
 #pragma unroll
             for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = X[l] * X[l] + Y[l] * Y[l] + Z[l] * Z[l];
-            real acc2 = 0;   // links with weight 2
-            for (int o = 0; o < O; ++o) {
-                const real* s = sm.sph + SPH_STRIDE * o;
-                const real k = s[3];
-                real ax, ay, az, b;
-                load4(s + 4, ax, ay, az, b);
-#pragma unroll
-                for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
-                    const real e = rbf_exp((real)1, X[l] * ax + (Y[l] * ay + (Z[l] * az + (k * PP[l] + b))));
-                    if (l == 2 || l == 4) acc2 += e; else acc += e;
-                }
-            }
-            acc += acc2 + acc2;
-        } else {
-            fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+            if (P.has_spheres) {
+                real acc = 0, acc2 = 0;   // acc2: links with weight 2
                 for (int o = 0; o < O; ++o) {
                     const real* s = sm.sph + SPH_STRIDE * o;
-                    const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
-                    acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
+                    const real k = s[3];
+                    real ax, ay, az, b;
+                    load4(s + 4, ax, ay, az, b);
+#pragma unroll
+                    for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
+                        const real e = rbf_exp((real)1, X[l] * ax + (Y[l] * ay + (Z[l] * az + (k * PP[l] + b))));
+                        if (l == 2 || l == 4) acc2 += e; else acc += e;
+                    }
                 }
-            });
+                c_coll += acc + (acc2 + acc2);
+            }
+            if (CHAIN == 2 && P.has_self) {   // CHAIN 2 = Panda structure with the self-collision code compiled in
+                // weights of the 6 evaluated origins: {1,1,2,1,2,1}; constants: base (w = include_base) and
+                // link1 = link2 at (0,0,z0) (w = 2).  Ordered pairs => every unordered pair counts twice.
+                const real ks = P.self_k, z0 = P.p[0][2];
+                real a1 = 0, a2 = 0, a4 = 0;     // sums of E over unordered pairs with weight product 1, 2, 4
+#pragma unroll
+                for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
+                    const bool w2 = (l == 2 || l == 4);
+                    const real e12 = rbf_exp(ks, PP[l] + z0 * (z0 - (real)2 * Z[l]));      // vs link1/link2 (w = 2)
+                    if (w2) a4 += e12; else a2 += e12;
+                    if (P.include_base) {
+                        const real eb = rbf_exp(ks, PP[l]);                                // vs base (w = 1)
+                        if (w2) a2 += eb; else a1 += eb;
+                    }
+#pragma unroll
+                    for (int m = l + 1; m < PANDA_EVAL_LINKS; ++m) {
+                        const real dx = X[l] - X[m], dy = Y[l] - Y[m], dz = Z[l] - Z[m];
+                        const real e = rbf_exp(ks, dx * dx + dy * dy + dz * dz);
+                        const int wp = (w2 ? 2 : 1) * ((m == 2 || m == 4) ? 2 : 1);
+                        if (wp == 4) a4 += e; else if (wp == 2) a2 += e; else a1 += e;
+                    }
+                }
+                c_self += (real)2 * (a1 + (real)2 * a2 + (real)4 * a4);
+            }
+        } else {
+            if (P.has_self) {
+                // generic chain: keep every origin, then the upper triangle of the pair matrix
+                real PX[SGPMP_MAX_FRAMES + 1], PY[SGPMP_MAX_FRAMES + 1], PZ[SGPMP_MAX_FRAMES + 1];
+                int L = 0;
+                real acc = 0;
+                fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+                    PX[L] = x; PY[L] = y; PZ[L] = z; ++L;
+                    if (P.has_spheres)
+                        for (int o = 0; o < O; ++o) {
+                            const real* s = sm.sph + SPH_STRIDE * o;
+                            const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
+                            acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
+                        }
+                });
+                c_coll += acc;
+                real sa = 0;
+                for (int l = 0; l < L; ++l)
+                    for (int m = l + 1; m < L; ++m) {
+                        const real dx = PX[l] - PX[m], dy = PY[l] - PY[m], dz = PZ[l] - PZ[m];
+                        sa += rbf_exp(P.self_k, dx * dx + dy * dy + dz * dz);
+                    }
+                c_self += (real)2 * sa + (real)L;
+            } else {
+                real acc = 0;
+                fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+                    for (int o = 0; o < O; ++o) {
+                        const real* s = sm.sph + SPH_STRIDE * o;
+                        const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
+                        acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
+                    }
+                });
+                c_coll += acc;
+            }
         }
-        return acc;
     }
 
     __device__ __forceinline__ real map_value(const CostParams<real>& P, const CostSmem<real>& sm, real x, real y) const {
@@ -244,7 +297,7 @@ struct TrajCost {
                 c_gp += P.q11 * ep * ep + P.q12x2 * ep * ev + P.q22 * ev * ev;
             }
             if (P.has_map) c_coll += map_value(P, sm, x[0], x[1]);
-            if (P.has_spheres) c_coll += link_sphere_rbf(P, sm, x);
+            if (P.has_spheres || P.has_self) link_fields(P, sm, x);
         }
         if (t == T - 1 && P.has_goal) {
 #pragma unroll
@@ -268,12 +321,17 @@ struct TrajCost {
     __device__ __forceinline__ void finish(const CostParams<real>& P, const CostSmem<real>& sm, int T) {
         c_start *= P.inv_sig_start2;
         c_goal *= P.inv_sig_goal2;
-        if (CHAIN == 1) c_coll += (real)(T - 1) * sm.coll_const;
+        if (CHAIN >= 1) {
+            c_coll += (real)(T - 1) * sm.coll_const;
+            c_self += (real)(T - 1) * sm.self_const;
+        }
         c_coll *= (P.has_map ? P.map_w_coll : P.sphere_w_coll);
+        c_self *= P.self_w_coll;
         c_is *= P.temperature;
     }
-    // reference summation order: CostGP (start + gp), CostGoalPrior, CostCollision, then += IS
-    __device__ __forceinline__ real total() const { return (((c_start + c_gp) + c_goal) + c_coll) + c_is; }
+    // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
+    // obstacle collision (examples/panda_environment.py:90), then += IS (planner.py:236)
+    __device__ __forceinline__ real total() const { return ((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_is; }
 };
 
 // Per-CTA staging of the problem constants into shared memory: start [d], goal [d] of goal index g, the sphere
@@ -294,7 +352,7 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
     __syncthreads();
     if (threadIdx.x == 0) {
         real cc = 0;
-        if (CHAIN == 1 && P.has_spheres) {
+        if (CHAIN >= 1 && P.has_spheres) {
             // q-independent origins of the Panda structure: base (if counted), link1 and link2 at (0, 0, z0)
             const real z0 = P.p[0][2];
             for (int o = 0; o < P.n_spheres; ++o) {
@@ -304,6 +362,13 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
             }
         }
         sph[SPH_STRIDE * SGPMP_MAX_SPHERES] = cc;
+        real sc = 0;
+        if (CHAIN >= 1 && P.has_self) {
+            // constant-constant pairs + the diagonal of the 6 evaluated origins (weights 1,1,2,1,2,1 -> 12)
+            const real z0 = P.p[0][2], wb = P.include_base ? (real)1 : (real)0;
+            sc = wb * wb + (real)4 + (real)4 * wb * rbf_exp(P.self_k, z0 * z0) + (real)12;
+        }
+        sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1] = sc;
     }
     __syncthreads();
 }

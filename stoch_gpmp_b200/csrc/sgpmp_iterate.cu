@@ -88,6 +88,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = bvec; sm.sph = sph;
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
+    sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     __syncthreads();
 
@@ -305,7 +306,8 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     A.means = (real*)means; A.means_pre = (real*)means_pre; A.samples = (real*)samples;
     A.costs = (real*)costs; A.weights = (real*)weights; A.grad = (real*)grad;
     if constexpr (sizeof(real) == 4) {
-        if (P.has_spheres && chain_is_panda_structure(desc, sh.n_dof)) return launch_iterate_n<real, 7, 1>(sh, P, A, st);
+        if ((P.has_spheres || P.has_self) && chain_is_panda_structure(desc, sh.n_dof))
+            return P.has_self ? launch_iterate_n<real, 7, 2>(sh, P, A, st) : launch_iterate_n<real, 7, 1>(sh, P, A, st);
     }
     switch (sh.n_dof) {
 #define SGPMP_DOF_CASE(N) case N: return launch_iterate_n<real, N, 0>(sh, P, A, st);

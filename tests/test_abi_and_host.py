@@ -133,7 +133,10 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
     ta = {'device': torch.device('cpu'), 'dtype': torch.float32}
     gp = CostGP(7, 8, torch.zeros(14), 0.05, dict(sigma_start=1., sigma_gp=1.), ta)
     with pytest.raises(NotImplementedError):
-        LinkSelfDistanceField()
+        LinkSelfDistanceField(num_interpolate=2).check_lowerable()
+    with pytest.raises(NotImplementedError, match="SerialChainFK"):
+        CostComposite(7, 8, [gp, CostCollision(7, 8, field=LinkSelfDistanceField(), sigma_coll=1.)], FK=None).lower(
+            1, 1, torch.device('cpu'), torch.float32)
     with pytest.raises(NotImplementedError):
         EESE3DistanceField(None)
     with pytest.raises(NotImplementedError):

@@ -50,6 +50,10 @@ def _lowered(spec, dev, dtype, B=1):
         cl.append(CostGoalPrior(n, T, multi_goal_states=torch.tensor(spec['goals'], **ta), num_particles_per_goal=spec['K'],
                                 num_samples=spec['S'], sigma_goal_prior=spec['sigma_goal_prior'], tensor_args=ta))
     FK = None
+    if spec.get('self_margin') is not None:
+        from stoch_gpmp_b200.costs.fields import LinkSelfDistanceField
+        FK = PandaFK()
+        cl.append(CostCollision(n, T, field=LinkSelfDistanceField(margin=spec['self_margin'], tensor_args=ta), sigma_coll=spec['sigma_self']))
     if 'map' in spec:
         H = spec['map'].shape[0]
         om = ObstacleMap([2, 2], 1.0, tensor_args=ta)
@@ -227,8 +231,10 @@ def test_cost_terms_match_reference(name, cuda):
             if 'map' in spec:
                 # integer index work: the occupancy sums must be bit-exact
                 assert np.array_equal(terms[3], g[pre + 'term_coll'])
-            else:
+            elif 'spheres' in spec:
                 assert rel(terms[3], g[pre + 'term_coll']) < (3e-5 if f32 else 10 * tol)
+        if spec.get('self_margin') is not None:
+            assert rel(terms[5], g[pre + 'term_self']) < (3e-5 if f32 else 10 * tol)
         # IS term: against the fp64 oracle everywhere; against the reference where the reference itself is
         # accurate (fp64).  The fp32 reference's IS term carries up to 4e-3 of cancellation noise.
         _, tot_o = OP.eval_costs(spec, g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O)
@@ -331,7 +337,7 @@ def test_fused_iteration_matches_reference(name, cuda):
         assert rel(from_sminor(out['samples'].cpu().numpy())[0], g[pre + 'samples']) < ftol
         costs = out['costs'].cpu().numpy()[0]
         if not f32:
-            assert rel(costs, g[pre + 'costs']) < 1e-10
+            assert rel(costs, g[pre + 'costs']) < max(ftol, 1e-10)
             assert np.abs(out['weights'].cpu().numpy()[0] - g[pre + 'weights']).max() < 1e-7
             assert rel(out['grad'].cpu().numpy()[0], g[pre + 'grad']) < max(10 * ftol, 1e-9)
             assert rel(mu.cpu().numpy()[0], g[pre + 'means_post']) < ftol

@@ -16,7 +16,7 @@ def test_port_reproduces_reference(name):
     g = load(name)
     spec = OP.spec_from_golden(g)
     dtype = torch.float32 if spec['dtype'] == 'float32' else torch.float64
-    port = ReferencePort(spec, dtype=dtype, fk=OFK.fk_all_links_torch() if 'spheres' in spec else None)
+    port = ReferencePort(spec, dtype=dtype, fk=OFK.fk_all_links_torch() if ('spheres' in spec or 'self_margin' in spec) else None)
     assert rel(port.Sigma_inv.numpy(), g['Sigma_inv']) < (1e-6 if dtype == torch.float32 else 1e-15)
     tol = 2e-3 if dtype == torch.float32 else 1e-9
     for it in range(n_iters(g)):
