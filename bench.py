@@ -312,11 +312,21 @@ def run_ours(args, rank, world, local_rank):
         measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic, ncu_facts = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json"))).get(w["name"])
+        if tj and tj["problems"] == B:
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+            ncu_facts = {k: tj[k] for k in ("thread_instructions_per_traj_sample", "issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct")}
+    except Exception:
+        pass
     flops, mufu = algorithmic_flops_per_traj(w)
     ach_tf = ntraj_rank * flops / (ms_per_step * 1e-3) / 1e12
     ach_mufu = ntraj_rank * mufu / (ms_per_step * 1e-3) / 1e12
-    roof = {"bound": "fp32", "kernel": "sgpmp::iterate_kernel<float,%d,256>" % w["n_dof"], "achieved": ach_tf,
-            "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["fp32_tflops"], "traffic": None,
+    roof = {"bound": "fp32", "kernel": "sgpmp::iterate_kernel<float,%d,256,%d>" % (w["n_dof"], 1 if w["spheres"] is not None else 0), "achieved": ach_tf,
+            "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["fp32_tflops"], "traffic": traffic,
+            "traffic_source": "profiles/r1/traffic.json (ncu --set full capture of this command)" if traffic else None,
+            "ncu": ncu_facts,
             "peak_source": "FP32 FMA probe kernel timed in this run (MEASURED_PEAKS.json has no FP32-pipe entry; nominal 74.4)",
             "algorithmic_flops_per_traj_sample": flops, "launch_ms": ms_per_step,
             "mufu": {"achieved_tops": ach_mufu, "peak_tops": peaks["mufu_tops"], "frac": ach_mufu / peaks["mufu_tops"],
