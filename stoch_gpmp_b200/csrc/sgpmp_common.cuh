@@ -72,25 +72,6 @@ inline bool shape_ok(const sgpmp_shape_t* s) {
 // precision-matched math wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ float sg_exp(float x) { return expf(x); }
 __device__ __forceinline__ double sg_exp(double x) { return exp(x); }
-// fp32 sincos for joint angles: branch-free, FMA pipe only (no MUFU, no slow path).  2-term Cody-Waite
-// reduction by pi/2 (exact enough for |x| < 1e3 rad) + the classic cephes single-precision minimax
-// polynomials on [-pi/4, pi/4]; max abs error 7e-8 on |x| <= 12 (emulated against fp64; test_fk_known_answers_cuda checks FK to 2e-6).
-// libdevice sincosf costs ~28 issue slots incl. a divergent slow-path guard; this is ~19.
-__device__ __forceinline__ void sg_sincos(float x, float* sp, float* cp) {
-    const float t = fmaf(x, 0.636619772367581f, 12582912.0f);   // 1.5 * 2^23: rint(x * 2/pi) lands in the low mantissa bits
-    const int q = __float_as_int(t);
-    const float j = t - 12582912.0f;
-    float r = fmaf(j, -1.5707963705062866f, x);        // pi/2 = C1 + C2 (+ 1.7e-15)
-    r = fmaf(j, 4.371138828673793e-08f, r);
-    const float z = r * r;
-    const float s = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
-    const float c = fmaf(fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z, -0.5f), z, 1.0f);
-    const float ss = (q & 1) ? c : s;
-    const float cc = (q & 1) ? s : c;
-    *sp = __int_as_float(__float_as_int(ss) ^ ((q << 30) & 0x80000000));
-    *cp = __int_as_float(__float_as_int(cc) ^ (((q + 1) << 30) & 0x80000000));
-}
-__device__ __forceinline__ void sg_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ __forceinline__ float sg_floor(float x) { return floorf(x); }
 __device__ __forceinline__ double sg_floor(double x) { return floor(x); }
 __device__ __forceinline__ float sg_max(float a, float b) { return fmaxf(a, b); }

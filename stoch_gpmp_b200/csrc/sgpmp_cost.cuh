@@ -15,18 +15,12 @@
 #include <math.h>
 
 #include "sgpmp_common.cuh"
+#include "sgpmp_vec.cuh"
 
 namespace sgpmp {
 
-__device__ __forceinline__ float fast_exp2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// exp(k * d2) for the sphere RBF.  fp32: k is pre-multiplied by log2(e) and evaluated with ex2.approx
-// (2 ulp; the RBF terms are in (0,1]); fp64: libdevice exp.
-__device__ __forceinline__ float rbf_exp(float k_log2e, float d2) { return fast_exp2(k_log2e * d2); }
-__device__ __forceinline__ double rbf_exp(double k, double d2) { return exp(k * d2); }
+// The sphere / self RBFs evaluate exp(k d^2) as vexp2_fast(k' d^2): in fp32 k' = k log2(e) and the exponential is
+// ex2.approx (2 ulp; the terms are in (0,1]); in fp64 k' = k and it is libdevice exp.
 
 // Per-CTA constants staged in shared memory by the caller.
 template <typename real>
@@ -63,137 +57,151 @@ __device__ __forceinline__ void stage_sphere(const real* s4, real* row) {
     row[7] = (real)(k * (cx * cx + cy * cy + cz * cz));
 }
 
+template <typename V> __device__ __forceinline__ V vneg(V a) { return -a; }
+template <> __device__ __forceinline__ F2 vneg<F2>(F2 a) { return f2(-lane0(a), -lane1(a)); }   // folds into operand modifiers
+
 // Forward kinematics of a serial arm (frames 0..N-1: fixed transform then revolute-z joint f; frames
 // N..n_frames-1 fixed), calling visit(x, y, z) for every link-frame origin in chain order
 // (base first if include_base).  Chain constants come from the kernel-parameter constant bank.
-template <typename real, int N, typename F>
-__device__ __forceinline__ void fk_visit_links(const CostParams<real>& P, const real* q, F&& visit) {
-    real R0 = 1, R1 = 0, R2 = 0, R3 = 0, R4 = 1, R5 = 0, R6 = 0, R7 = 0, R8 = 1;
-    real px = 0, py = 0, pz = 0;
+// V: scalar real or F2 (two samples per thread).
+template <typename V, int N, typename F>
+__device__ __forceinline__ void fk_visit_links(const CostParams<typename VT<V>::real>& P, const V* q, F&& visit) {
+    using real = typename VT<V>::real;
+    const V one = vbroadcast<V>((real)1), zero = vbroadcast<V>((real)0);
+    V R0 = one, R1 = zero, R2 = zero, R3 = zero, R4 = one, R5 = zero, R6 = zero, R7 = zero, R8 = one;
+    V px = zero, py = zero, pz = zero;
     if (P.include_base) visit(px, py, pz);
+    auto fixed = [&](int f) {
+        const real* F_ = P.R[f];
+        const real* tf = P.p[f];
+        px = vfma(R0, tf[0], vfma(R1, tf[1], vfma(R2, tf[2], px)));
+        py = vfma(R3, tf[0], vfma(R4, tf[1], vfma(R5, tf[2], py)));
+        pz = vfma(R6, tf[0], vfma(R7, tf[1], vfma(R8, tf[2], pz)));
+        // R <- R * F
+        const V a0 = vfma(R0, F_[0], vfma(R1, F_[3], R2 * F_[6])), a1 = vfma(R0, F_[1], vfma(R1, F_[4], R2 * F_[7])), a2 = vfma(R0, F_[2], vfma(R1, F_[5], R2 * F_[8]));
+        const V a3 = vfma(R3, F_[0], vfma(R4, F_[3], R5 * F_[6])), a4 = vfma(R3, F_[1], vfma(R4, F_[4], R5 * F_[7])), a5 = vfma(R3, F_[2], vfma(R4, F_[5], R5 * F_[8]));
+        const V a6 = vfma(R6, F_[0], vfma(R7, F_[3], R8 * F_[6])), a7 = vfma(R6, F_[1], vfma(R7, F_[4], R8 * F_[7])), a8 = vfma(R6, F_[2], vfma(R7, F_[5], R8 * F_[8]));
+        R0 = a0; R1 = a1; R2 = a2; R3 = a3; R4 = a4; R5 = a5; R6 = a6; R7 = a7; R8 = a8;
+    };
 #pragma unroll
     for (int f = 0; f < N; ++f) {
-        const real* F_ = P.R[f];
-        const real* tf = P.p[f];
-        px += R0 * tf[0] + R1 * tf[1] + R2 * tf[2];
-        py += R3 * tf[0] + R4 * tf[1] + R5 * tf[2];
-        pz += R6 * tf[0] + R7 * tf[1] + R8 * tf[2];
-        // R <- R * F
-        const real a0 = R0 * F_[0] + R1 * F_[3] + R2 * F_[6], a1 = R0 * F_[1] + R1 * F_[4] + R2 * F_[7], a2 = R0 * F_[2] + R1 * F_[5] + R2 * F_[8];
-        const real a3 = R3 * F_[0] + R4 * F_[3] + R5 * F_[6], a4 = R3 * F_[1] + R4 * F_[4] + R5 * F_[7], a5 = R3 * F_[2] + R4 * F_[5] + R5 * F_[8];
-        const real a6 = R6 * F_[0] + R7 * F_[3] + R8 * F_[6], a7 = R6 * F_[1] + R7 * F_[4] + R8 * F_[7], a8 = R6 * F_[2] + R7 * F_[5] + R8 * F_[8];
-        // R <- R * Rz(q_f): col0' = c col0 + s col1, col1' = -s col0 + c col1
-        real s, c;
-        sg_sincos(q[f], &s, &c);
-        R0 = c * a0 + s * a1; R1 = c * a1 - s * a0; R2 = a2;
-        R3 = c * a3 + s * a4; R4 = c * a4 - s * a3; R5 = a5;
-        R6 = c * a6 + s * a7; R7 = c * a7 - s * a6; R8 = a8;
+        fixed(f);
+        // R <- R * Rz(q_f): col0' = c col0 + s col1, col1' = c col1 - s col0
+        V s, c;
+        vsincos(q[f], &s, &c);
+        const V n0 = vfma(c, R0, s * R1), n3 = vfma(c, R3, s * R4), n6 = vfma(c, R6, s * R7);
+        R1 = vfma(c, R1, vneg(s * R0)); R4 = vfma(c, R4, vneg(s * R3)); R7 = vfma(c, R7, vneg(s * R6));
+        R0 = n0; R3 = n3; R6 = n6;
         visit(px, py, pz);
     }
-    // fixed tail frames (only positions are needed downstream)
-    for (int f = N; f < P.n_frames; ++f) {
-        const real* F_ = P.R[f];
-        const real* tf = P.p[f];
-        px += R0 * tf[0] + R1 * tf[1] + R2 * tf[2];
-        py += R3 * tf[0] + R4 * tf[1] + R5 * tf[2];
-        pz += R6 * tf[0] + R7 * tf[1] + R8 * tf[2];
-        const real a0 = R0 * F_[0] + R1 * F_[3] + R2 * F_[6], a1 = R0 * F_[1] + R1 * F_[4] + R2 * F_[7], a2 = R0 * F_[2] + R1 * F_[5] + R2 * F_[8];
-        const real a3 = R3 * F_[0] + R4 * F_[3] + R5 * F_[6], a4 = R3 * F_[1] + R4 * F_[4] + R5 * F_[7], a5 = R3 * F_[2] + R4 * F_[5] + R5 * F_[8];
-        const real a6 = R6 * F_[0] + R7 * F_[3] + R8 * F_[6], a7 = R6 * F_[1] + R7 * F_[4] + R8 * F_[7], a8 = R6 * F_[2] + R7 * F_[5] + R8 * F_[8];
-        R0 = a0; R1 = a1; R2 = a2; R3 = a3; R4 = a4; R5 = a5; R6 = a6; R7 = a7; R8 = a8;
+    for (int f = N; f < P.n_frames; ++f) {   // fixed tail frames (only positions are needed downstream)
+        fixed(f);
         visit(px, py, pz);
     }
 }
 
 // ---- structured chains ------------------------------------------------------------------------------
 // CHAIN = 0: generic serial arm (fk_visit_links, runtime constants).
-// CHAIN = 1 (spheres only) / 2 (+ self-collision code): "Panda structure" (7 joints): fixed rotations are identity / Rx(+-90 deg) / about-z, and most
-// translation components are zero (panda_arm_no_gripper.urdf).  The STRUCTURE is compile-time — Rx(+-90)
-// becomes a signed relabelling of columns, zero translation components vanish — while the translation VALUES
-// still come from the descriptor.  The host selects it only when the descriptor matches this structure
-// (cos(1.57079632679) = 4.9e-12 is below fp32 resolution; fp64 always uses the generic path).
-// Further structure used: frames with zero translation share their parent's origin (evaluated once, weight
-// 2); origins that do not depend on q (base, link1, link2) are folded into CostSmem::coll_const; joint 7 only
-// spins the z axis along which the remaining translations point, so q[6] is never needed.
+// CHAIN = 1 (spheres only) / 2 (+ self-collision code): "Panda structure" (7 joints): fixed rotations are
+// identity / Rx(+-90 deg) / about-z, and most translation components are zero (panda_arm_no_gripper.urdf).
+// The STRUCTURE is compile-time — Rx(+-90) becomes a signed relabelling of columns, zero translation components
+// vanish, the first two joints are expanded by hand — while the translation VALUES still come from the
+// descriptor.  The host selects it only when the descriptor matches this structure (cos(1.57079632679) =
+// 4.9e-12 is below fp32 resolution; fp64 always uses the generic path).  Further structure used: frames with
+// zero translation share their parent's origin (evaluated once, weight 2); origins that do not depend on q
+// (base, link1, link2) are folded into CostSmem::coll_const; joint 7 only spins the z axis along which the
+// remaining translations point, so q[6] is never needed.
 constexpr int PANDA_EVAL_LINKS = 6;   // link3, link4, link5(=link6), link7, link8(=hand), ee
 
-template <typename real>
-struct Cols {   // rotation columns
-    real ax, ay, az, bx, by, bz, cx, cy, cz;
+template <typename V>
+struct Cols {   // rotation columns a, b, c
+    V ax, ay, az, bx, by, bz, cx, cy, cz;
     __device__ __forceinline__ void rot_xp90() {   // R <- R Rx(+90): (a, b, c) -> (a, c, -b)
-        const real tx = bx, ty = by, tz = bz;
+        const V tx = bx, ty = by, tz = bz;
         bx = cx; by = cy; bz = cz;
-        cx = -tx; cy = -ty; cz = -tz;
+        cx = vneg(tx); cy = vneg(ty); cz = vneg(tz);
     }
     __device__ __forceinline__ void rot_xm90() {   // R <- R Rx(-90): (a, b, c) -> (a, -c, b)
-        const real tx = bx, ty = by, tz = bz;
-        bx = -cx; by = -cy; bz = -cz;
+        const V tx = bx, ty = by, tz = bz;
+        bx = vneg(cx); by = vneg(cy); bz = vneg(cz);
         cx = tx; cy = ty; cz = tz;
     }
-    __device__ __forceinline__ void rot_z(real q) {  // R <- R Rz(q)
-        real s, c;
-        sg_sincos(q, &s, &c);
-        const real nax = c * ax + s * bx, nay = c * ay + s * by, naz = c * az + s * bz;
-        bx = c * bx - s * ax; by = c * by - s * ay; bz = c * bz - s * az;
+    __device__ __forceinline__ void rot_z(V q) {  // R <- R Rz(q): a' = c a + s b, b' = c b - s a
+        V s, c;
+        vsincos(q, &s, &c);
+        rot_z_sc(s, c);
+    }
+    __device__ __forceinline__ void rot_z_sc(V s, V c) {
+        const V nax = vfma(c, ax, s * bx), nay = vfma(c, ay, s * by), naz = vfma(c, az, s * bz);
+        bx = vfma(c, bx, vneg(s * ax)); by = vfma(c, by, vneg(s * ay)); bz = vfma(c, bz, vneg(s * az));
         ax = nax; ay = nay; az = naz;
     }
 };
 
 // Origins of the 6 q-dependent, distinct link frames of the Panda structure; weights {1,1,2,1,2,1}.
-template <typename real>
-__device__ __forceinline__ void fk_panda_origins(const CostParams<real>& P, const real* q, real (&X)[PANDA_EVAL_LINKS],
-                                                 real (&Y)[PANDA_EVAL_LINKS], real (&Z)[PANDA_EVAL_LINKS]) {
-    Cols<real> R{1, 0, 0, 0, 1, 0, 0, 0, 1};
-    real px = 0, py = 0, pz = P.p[0][2];           // frame 0: t = (0,0,z), rot = I
-    R.rot_z(q[0]);
-    R.rot_xm90();                                  // frame 1: t = 0, Rx(-90)
-    R.rot_z(q[1]);
-    px += P.p[2][1] * R.bx; py += P.p[2][1] * R.by; pz += P.p[2][1] * R.bz;   // frame 2: t = (0,y,0), Rx(+90)
+template <typename V>
+__device__ __forceinline__ void fk_panda_origins(const CostParams<typename VT<V>::real>& P, const V* q, V (&X)[PANDA_EVAL_LINKS],
+                                                 V (&Y)[PANDA_EVAL_LINKS], V (&Z)[PANDA_EVAL_LINKS]) {
+    using real = typename VT<V>::real;
+    // joints 1 and 2 by hand (R starts as the identity; frame 0: t = (0,0,d1); frame 1: t = 0, Rx(-90)):
+    //   a = (c1 c0, c1 s0, -s1), b = (-s1 c0, -s1 s0, -c1), c = (-s0, c0, 0),  p = (0, 0, d1)
+    V s0, c0, s1, c1;
+    vsincos(q[0], &s0, &c0);
+    vsincos(q[1], &s1, &c1);
+    const real d1 = P.p[0][2], t2y = P.p[2][1];
+    const V s1c0 = s1 * c0, s1s0 = s1 * s0;
+    V px = (-t2y) * s1c0, py = (-t2y) * s1s0, pz = vfma(-t2y, c1, d1);          // frame 2: p += t2y * b
     X[0] = px; Y[0] = py; Z[0] = pz;               // link3
-    R.rot_xp90();
+    // frame 2 rotation Rx(+90): (a, b, c) -> (a, c, -b)
+    Cols<V> R;
+    R.ax = c1 * c0; R.ay = c1 * s0; R.az = vneg(s1);
+    R.bx = vneg(s0); R.by = c0; R.bz = vbroadcast<V>((real)0);
+    R.cx = s1c0; R.cy = s1s0; R.cz = c1;
     R.rot_z(q[2]);
-    px += P.p[3][0] * R.ax; py += P.p[3][0] * R.ay; pz += P.p[3][0] * R.az;   // frame 3: t = (x,0,0), Rx(+90)
+    px = vfma(P.p[3][0], R.ax, px); py = vfma(P.p[3][0], R.ay, py); pz = vfma(P.p[3][0], R.az, pz);   // frame 3: t = (x,0,0), Rx(+90)
     X[1] = px; Y[1] = py; Z[1] = pz;               // link4
     R.rot_xp90();
     R.rot_z(q[3]);
-    px += P.p[4][0] * R.ax + P.p[4][1] * R.bx;                                 // frame 4: t = (x,y,0), Rx(-90)
-    py += P.p[4][0] * R.ay + P.p[4][1] * R.by;
-    pz += P.p[4][0] * R.az + P.p[4][1] * R.bz;
+    px = vfma(P.p[4][0], R.ax, vfma(P.p[4][1], R.bx, px));                                             // frame 4: t = (x,y,0), Rx(-90)
+    py = vfma(P.p[4][0], R.ay, vfma(P.p[4][1], R.by, py));
+    pz = vfma(P.p[4][0], R.az, vfma(P.p[4][1], R.bz, pz));
     X[2] = px; Y[2] = py; Z[2] = pz;               // link5 (= link6: frame 5 has t = 0)
     R.rot_xm90();
     R.rot_z(q[4]);
     R.rot_xp90();                                  // frame 5: t = 0, Rx(+90)
     R.rot_z(q[5]);
-    px += P.p[6][0] * R.ax; py += P.p[6][0] * R.ay; pz += P.p[6][0] * R.az;   // frame 6: t = (x,0,0), Rx(+90)
+    px = vfma(P.p[6][0], R.ax, px); py = vfma(P.p[6][0], R.ay, py); pz = vfma(P.p[6][0], R.az, pz);   // frame 6: t = (x,0,0), Rx(+90)
     X[3] = px; Y[3] = py; Z[3] = pz;               // link7
-    R.rot_xp90();                                  // joint 7 spins about c: c unchanged, q[6] not needed
-    px += P.p[7][2] * R.cx; py += P.p[7][2] * R.cy; pz += P.p[7][2] * R.cz;   // frame 7: t = (0,0,z)
+    // frame 6 rotation Rx(+90) makes the new z column -b; joint 7 spins about it, so q[6] is not needed
+    px = vfma(-P.p[7][2], R.bx, px); py = vfma(-P.p[7][2], R.by, py); pz = vfma(-P.p[7][2], R.bz, pz); // frame 7: t = (0,0,z)
     X[4] = px; Y[4] = py; Z[4] = pz;               // link8 (= hand: frame 8 has t = 0, rotation about z)
-    px += P.p[9][2] * R.cx; py += P.p[9][2] * R.cy; pz += P.p[9][2] * R.cz;   // frame 9: t = (0,0,z), about z
+    px = vfma(-P.p[9][2], R.bx, px); py = vfma(-P.p[9][2], R.by, py); pz = vfma(-P.p[9][2], R.bz, pz); // frame 9: t = (0,0,z), about z
     X[5] = px; Y[5] = py; Z[5] = pz;               // ee_link
 }
 
-template <typename real, int N, int CHAIN = 0>
+template <typename V, int N, int CHAIN = 0>
 struct TrajCost {
-    real c_start, c_gp, c_goal, c_coll, c_is, c_self;
-    real xp[2 * N];   // previous state
+    using real = typename VT<V>::real;
+    V c_start, c_gp, c_goal, c_coll, c_is, c_self;
+    V xp[2 * N];   // previous state
 
-    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = 0; }
+    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = vbroadcast<V>((real)0); }
 
     // Link fields of configuration q (one FK evaluation shared by both):
     //   spheres  sum_l sum_o exp(-0.5 |p_l - c_o|^2 / r_o^2)            LinkDistanceField 'rbf'   costs/fields.py:63-79
     //   self     sum_{i,j} exp(-|p_i - p_j|^2 / (2 margin^2)), all ordered pairs incl. i == j
     //                                                                    LinkSelfDistanceField     costs/fields.py:114-124
-    __device__ __forceinline__ void link_fields(const CostParams<real>& P, const CostSmem<real>& sm, const real* q) {
+    __device__ __forceinline__ void link_fields(const CostParams<real>& P, const CostSmem<real>& sm, const V* q) {
         const int O = P.n_spheres;
+        const V zero = vbroadcast<V>((real)0);
         if constexpr (CHAIN >= 1) {
             static_assert(N == 7, "Panda structure has 7 joints");
-            real X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS], PP[PANDA_EVAL_LINKS];
-            fk_panda_origins<real>(P, q, X, Y, Z);
+            V X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS], PP[PANDA_EVAL_LINKS];
+            fk_panda_origins<V>(P, q, X, Y, Z);
 #pragma unroll
-            for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = X[l] * X[l] + Y[l] * Y[l] + Z[l] * Z[l];
+            for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = vfma(X[l], X[l], vfma(Y[l], Y[l], Z[l] * Z[l]));
             if (P.has_spheres) {
-                real acc = 0, acc2 = 0;   // acc2: links with weight 2
+                V acc = zero, acc2 = zero;   // acc2: links with weight 2
                 for (int o = 0; o < O; ++o) {
                     const real* s = sm.sph + SPH_STRIDE * o;
                     const real k = s[3];
@@ -201,7 +209,7 @@ struct TrajCost {
                     load4(s + 4, ax, ay, az, b);
 #pragma unroll
                     for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
-                        const real e = rbf_exp((real)1, X[l] * ax + (Y[l] * ay + (Z[l] * az + (k * PP[l] + b))));
+                        const V e = vexp2_fast(vfma(X[l], ax, vfma(Y[l], ay, vfma(Z[l], az, vfma(PP[l], k, b)))));
                         if (l == 2 || l == 4) acc2 += e; else acc += e;
                     }
                 }
@@ -211,66 +219,62 @@ struct TrajCost {
                 // weights of the 6 evaluated origins: {1,1,2,1,2,1}; constants: base (w = include_base) and
                 // link1 = link2 at (0,0,z0) (w = 2).  Ordered pairs => every unordered pair counts twice.
                 const real ks = P.self_k, z0 = P.p[0][2];
-                real a1 = 0, a2 = 0, a4 = 0;     // sums of E over unordered pairs with weight product 1, 2, 4
+                V a1 = zero, a2 = zero, a4 = zero;     // sums of E over unordered pairs with weight product 1, 2, 4
 #pragma unroll
                 for (int l = 0; l < PANDA_EVAL_LINKS; ++l) {
                     const bool w2 = (l == 2 || l == 4);
-                    const real e12 = rbf_exp(ks, PP[l] + z0 * (z0 - (real)2 * Z[l]));      // vs link1/link2 (w = 2)
+                    const V e12 = vexp2_fast(ks * vfma((real)-2 * z0, Z[l], PP[l] + z0 * z0));    // vs link1/link2 (w = 2)
                     if (w2) a4 += e12; else a2 += e12;
                     if (P.include_base) {
-                        const real eb = rbf_exp(ks, PP[l]);                                // vs base (w = 1)
+                        const V eb = vexp2_fast(ks * PP[l]);                                       // vs base (w = 1)
                         if (w2) a2 += eb; else a1 += eb;
                     }
 #pragma unroll
                     for (int m = l + 1; m < PANDA_EVAL_LINKS; ++m) {
-                        const real dx = X[l] - X[m], dy = Y[l] - Y[m], dz = Z[l] - Z[m];
-                        const real e = rbf_exp(ks, dx * dx + dy * dy + dz * dz);
+                        const V dx = X[l] - X[m], dy = Y[l] - Y[m], dz = Z[l] - Z[m];
+                        const V e = vexp2_fast(ks * vfma(dx, dx, vfma(dy, dy, dz * dz)));
                         const int wp = (w2 ? 2 : 1) * ((m == 2 || m == 4) ? 2 : 1);
                         if (wp == 4) a4 += e; else if (wp == 2) a2 += e; else a1 += e;
                     }
                 }
-                c_self += (real)2 * (a1 + (real)2 * a2 + (real)4 * a4);
+                c_self += (real)2 * (a1 + ((real)2 * a2 + (real)4 * a4));
             }
         } else {
+            auto spheres_at = [&](V x, V y, V z, V& acc) {
+                for (int o = 0; o < O; ++o) {
+                    const real* s = sm.sph + SPH_STRIDE * o;
+                    const V dx = x - s[0], dy = y - s[1], dz = z - s[2];
+                    acc += vexp2_fast(s[3] * vfma(dx, dx, vfma(dy, dy, dz * dz)));
+                }
+            };
             if (P.has_self) {
                 // generic chain: keep every origin, then the upper triangle of the pair matrix
-                real PX[SGPMP_MAX_FRAMES + 1], PY[SGPMP_MAX_FRAMES + 1], PZ[SGPMP_MAX_FRAMES + 1];
+                V PX[SGPMP_MAX_FRAMES + 1], PY[SGPMP_MAX_FRAMES + 1], PZ[SGPMP_MAX_FRAMES + 1];
                 int L = 0;
-                real acc = 0;
-                fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
+                V acc = zero;
+                fk_visit_links<V, N>(P, q, [&](V x, V y, V z) {
                     PX[L] = x; PY[L] = y; PZ[L] = z; ++L;
-                    if (P.has_spheres)
-                        for (int o = 0; o < O; ++o) {
-                            const real* s = sm.sph + SPH_STRIDE * o;
-                            const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
-                            acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
-                        }
+                    if (P.has_spheres) spheres_at(x, y, z, acc);
                 });
                 c_coll += acc;
-                real sa = 0;
+                V sa = zero;
                 for (int l = 0; l < L; ++l)
                     for (int m = l + 1; m < L; ++m) {
-                        const real dx = PX[l] - PX[m], dy = PY[l] - PY[m], dz = PZ[l] - PZ[m];
-                        sa += rbf_exp(P.self_k, dx * dx + dy * dy + dz * dz);
+                        const V dx = PX[l] - PX[m], dy = PY[l] - PY[m], dz = PZ[l] - PZ[m];
+                        sa += vexp2_fast(P.self_k * vfma(dx, dx, vfma(dy, dy, dz * dz)));
                     }
                 c_self += (real)2 * sa + (real)L;
             } else {
-                real acc = 0;
-                fk_visit_links<real, N>(P, q, [&](real x, real y, real z) {
-                    for (int o = 0; o < O; ++o) {
-                        const real* s = sm.sph + SPH_STRIDE * o;
-                        const real dx = x - s[0], dy = y - s[1], dz = z - s[2];
-                        acc += rbf_exp(s[3], dx * dx + dy * dy + dz * dz);
-                    }
-                });
+                V acc = zero;
+                fk_visit_links<V, N>(P, q, [&](V x, V y, V z) { spheres_at(x, y, z, acc); });
                 c_coll += acc;
             }
         }
     }
 
-    __device__ __forceinline__ real map_value(const CostParams<real>& P, const CostSmem<real>& sm, real x, real y) const {
-        // X*(1/cell) + offset with two roundings, floor, int, clamp; value = map[iy][ix].  The reference
-        // clamps ix with shape[0] and iy with shape[1] (obst_map.py:177-178); maps are square here.
+    // X*(1/cell) + offset with two roundings, floor, int, clamp; value = map[iy][ix].  The reference clamps ix
+    // with shape[0] and iy with shape[1] (obst_map.py:177-178); maps are square here.
+    __device__ __forceinline__ real map_value1(const CostParams<real>& P, const CostSmem<real>& sm, real x, real y) const {
         const real xo = sg_mul_add_2r(x, P.map_inv_cell, P.map_origin_x);
         const real yo = sg_mul_add_2r(y, P.map_inv_cell, P.map_origin_y);
         int ix = (int)sg_floor(xo), iy = (int)sg_floor(yo);
@@ -278,23 +282,31 @@ struct TrajCost {
         iy = min(max(iy, 0), P.map_w - 1);
         return __ldg(sm.map + (size_t)iy * P.map_w + ix);
     }
+    __device__ __forceinline__ V map_value(const CostParams<real>& P, const CostSmem<real>& sm, V x, V y) const {
+        if constexpr (VT<V>::W == 2) {
+            return f2(map_value1(P, sm, vlane(x, 0), vlane(y, 0)), map_value1(P, sm, vlane(x, 1), vlane(y, 1)));
+        } else {
+            return map_value1(P, sm, x, y);
+        }
+    }
 
     // feed state x_t (t = 0..T-1 in order)
     // brow: b_t = (Sigma^-1 mu)_t of this particle (2N reals, 16-byte aligned when 2N % 4 == 0 rows are padded), or null
     __device__ __forceinline__ void step(const CostParams<real>& P, const CostSmem<real>& sm, int t, int T,
-                                         const real (&x)[2 * N], const real* brow) {
+                                         const V (&x)[2 * N], const real* brow) {
         if (t == 0) {
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) {
-                const real e = sm.start[j] - x[j];
-                c_start += e * e;
+                const V e = sm.start[j] - x[j];
+                c_start = vfma(e, e, c_start);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const real ep = x[i] - xp[i] - P.dt * xp[N + i];
-                const real ev = x[N + i] - xp[N + i];
-                c_gp += P.q11 * ep * ep + P.q12x2 * ep * ev + P.q22 * ev * ev;
+                const V ep = vfma(-P.dt, xp[N + i], x[i] - xp[i]);
+                const V ev = x[N + i] - xp[N + i];
+                c_gp = vfma(ep, vfma(P.q12x2, ev, P.q11 * ep), c_gp);
+                c_gp = vfma(P.q22 * ev, ev, c_gp);
             }
             if (P.has_map) c_coll += map_value(P, sm, x[0], x[1]);
             if (P.has_spheres || P.has_self) link_fields(P, sm, x);
@@ -302,8 +314,8 @@ struct TrajCost {
         if (t == T - 1 && P.has_goal) {
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) {
-                const real e = sm.goal[j] - x[j];
-                c_goal += e * e;
+                const V e = sm.goal[j] - x[j];
+                c_goal = vfma(e, e, c_goal);
             }
         }
         if (brow) {
@@ -312,39 +324,43 @@ struct TrajCost {
 #pragma unroll
             for (int k = 0; k < DP4; ++k) load4(brow + 4 * k, b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
 #pragma unroll
-            for (int j = 0; j < 2 * N; ++j) c_is += x[j] * b[j];
+            for (int j = 0; j < 2 * N; ++j) c_is = vfma(x[j], b[j], c_is);
         }
 #pragma unroll
         for (int j = 0; j < 2 * N; ++j) xp[j] = x[j];
     }
 
     __device__ __forceinline__ void finish(const CostParams<real>& P, const CostSmem<real>& sm, int T) {
-        c_start *= P.inv_sig_start2;
-        c_goal *= P.inv_sig_goal2;
+        c_start = c_start * P.inv_sig_start2;
+        c_goal = c_goal * P.inv_sig_goal2;
         if (CHAIN >= 1) {
-            c_coll += (real)(T - 1) * sm.coll_const;
-            c_self += (real)(T - 1) * sm.self_const;
+            c_coll = c_coll + (real)(T - 1) * sm.coll_const;
+            c_self = c_self + (real)(T - 1) * sm.self_const;
         }
-        c_coll *= (P.has_map ? P.map_w_coll : P.sphere_w_coll);
-        c_self *= P.self_w_coll;
-        c_is *= P.temperature;
+        c_coll = c_coll * (P.has_map ? P.map_w_coll : P.sphere_w_coll);
+        c_self = c_self * P.self_w_coll;
+        c_is = c_is * P.temperature;
     }
     // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
     // obstacle collision (examples/panda_environment.py:90), then += IS (planner.py:236)
-    __device__ __forceinline__ real total() const { return ((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_is; }
+    __device__ __forceinline__ V total() const { return ((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_is; }
 };
 
 // Per-CTA staging of the problem constants into shared memory: start [d], goal [d] of goal index g, the sphere
 // table [MAX_SPHERES][8] followed by one slot for coll_const.  Ends with a __syncthreads().
 constexpr int SPH_SMEM = SPH_STRIDE * SGPMP_MAX_SPHERES + 4;   // keeps what follows 16-byte aligned
 
-template <typename real, int N, int CHAIN>
+// VOFF: offset of the velocity half inside the staged start/goal rows (N = dense; the dof-pair kernels pad it).
+template <typename real, int N, int CHAIN, int VOFF = N>
 __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, int b, int g, int G, real* start, real* goal,
                                                     real* sph) {
     constexpr int d = 2 * N;
+    for (int k = threadIdx.x; k < 2 * VOFF; k += blockDim.x) { start[k] = 0; goal[k] = 0; }
+    __syncthreads();
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
-        start[k] = P.start[(size_t)b * d + k];
-        goal[k] = P.has_goal ? P.goals[((size_t)b * G + g) * d + k] : (real)0;
+        const int c = k < N ? k : VOFF + (k - N);
+        start[c] = P.start[(size_t)b * d + k];
+        goal[c] = P.has_goal ? P.goals[((size_t)b * G + g) * d + k] : (real)0;
     }
     if (P.has_spheres)
         for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x)
@@ -357,8 +373,8 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
             const real z0 = P.p[0][2];
             for (int o = 0; o < P.n_spheres; ++o) {
                 const real* s = sph + SPH_STRIDE * o;
-                if (P.include_base) cc += rbf_exp((real)1, s[7]);
-                cc += (real)2 * rbf_exp((real)1, z0 * s[6] + (s[3] * z0 * z0 + s[7]));
+                if (P.include_base) cc += vexp2_fast(s[7]);
+                cc += (real)2 * vexp2_fast(z0 * s[6] + (s[3] * z0 * z0 + s[7]));
             }
         }
         sph[SPH_STRIDE * SGPMP_MAX_SPHERES] = cc;
@@ -366,7 +382,7 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
         if (CHAIN >= 1 && P.has_self) {
             // constant-constant pairs + the diagonal of the 6 evaluated origins (weights 1,1,2,1,2,1 -> 12)
             const real z0 = P.p[0][2], wb = P.include_base ? (real)1 : (real)0;
-            sc = wb * wb + (real)4 + (real)4 * wb * rbf_exp(P.self_k, z0 * z0) + (real)12;
+            sc = wb * wb + (real)4 + (real)4 * wb * vexp2_fast(P.self_k * z0 * z0) + (real)12;
         }
         sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1] = sc;
     }
@@ -399,11 +415,12 @@ inline int chain_is_panda_structure(const sgpmp_cost_desc_t& d, int n_dof) {
 // b = P mu for one particle, computed in fp64 from the D/O blocks (the fp32 reference evaluates this
 // contraction with catastrophic cancellation), stored as `real`.
 // tabDO: [T][7] doubles (d11,d12,d22,o11,o12,o21,o22), O_t = P[t+1,t].
-// MU_STRIDE: row stride of mu in reals (0 = dense rows of 2n).
-template <typename real, int MU_STRIDE = 0>
-__device__ __forceinline__ void precision_times_row(const double* tabDO, const real* mu, int T, int n, int t, int i,
+// MU_STRIDE: row stride of mu in reals (0 = dense rows of 2n); VOFF: offset of the velocity half (0 = n).
+template <typename real, int MU_STRIDE = 0, int VOFF = 0>
+__device__ __forceinline__ void precision_times_row(const double* tabDO, const real* mu, int T, int n_, int t, int i,
                                                     real* bp, real* bv) {
-    const int d = MU_STRIDE ? MU_STRIDE : 2 * n;
+    const int d = MU_STRIDE ? MU_STRIDE : 2 * n_;
+    const int n = VOFF ? VOFF : n_;
     const double* r = tabDO + t * 7;
     const double mp = mu[t * d + i], mv = mu[t * d + n + i];
     double p = r[0] * mp + r[1] * mv;

@@ -20,6 +20,7 @@
 
 #include "sgpmp_common.cuh"
 #include "sgpmp_cost.cuh"
+#include "sgpmp_cost_pairs.cuh"
 #include "sgpmp_rng.cuh"
 
 #ifndef SGPMP_MINB128
@@ -27,6 +28,9 @@
 #endif
 #ifndef SGPMP_MINB256
 #define SGPMP_MINB256 3
+#endif
+#ifndef SGPMP_MINB_PACKED
+#define SGPMP_MINB_PACKED 2
 #endif
 
 namespace sgpmp {
@@ -47,11 +51,23 @@ struct IterArgs {
     real* grad;            // optional, last iteration
 };
 
-template <typename real, int N, int BS, int CHAIN>
-__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (BS == 128 ? SGPMP_MINB128 : SGPMP_MINB256) : 1))
+// PACK selects the pass-1 arithmetic:
+//   0  scalar: one sample per thread (fp32 or fp64)
+//   1  two fp32 samples per thread, packed FFMA2/FADD2/FMUL2 across the two samples (sgpmp_vec.cuh)
+//   2  one fp32 sample per thread, packed arithmetic across neighbouring DoFs / links (sgpmp_cost_pairs.cuh)
+template <typename real, int PACK> struct PackV { using type = real; };
+template <> struct PackV<float, 1> { using type = F2; };
+
+template <typename real, int PACK, int N, int BS, int CHAIN>
+__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (PACK == 1 ? SGPMP_MINB_PACKED : (BS == 128 ? SGPMP_MINB128 : SGPMP_MINB256)) : 1))
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
+    using V = typename PackV<real, PACK>::type;
+    constexpr int W = VT<V>::W;
     constexpr int d = 2 * N;
-    constexpr int DP = (d + 3) & ~3;      // padded row length of mu / b: rows stay 16-byte aligned for LDS.128
+    constexpr int NP2 = (N + 1) / 2;
+    constexpr int VOFF = (PACK == 2) ? 2 * NP2 : N;                   // offset of the velocity half in a shared-memory row
+    constexpr int DP = (PACK == 2) ? 2 * VOFF : ((d + 3) & ~3);       // padded row length of mu / b (16-byte aligned rows)
+    auto col = [](int j) { return j < N ? j : VOFF + (j - N); };      // external state index -> shared-memory column
     const int T = A.T, S = A.S, G = A.G, K = A.K;
     const int TP = (T + 1) >> 1;
     const int M = T * d;
@@ -65,8 +81,8 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     real* wsm = acc + M;                                      // [S]
     real* part = wsm + S;                                     // [4*BS] partial sums of pass 2
     real* red = part + 4 * BS;                                // [32]
-    real* start = red + 32;                                   // [d]
-    real* goal = start + d;                                   // [d]
+    real* start = red + 32;                                   // [2*VOFF]
+    real* goal = start + 2 * VOFF;                            // [2*VOFF]
 
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
@@ -79,12 +95,10 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         tabGH[k] = c < 7 ? (real)row[c] : (real)0;
         if (c < 7) tabDO[t * 7 + c] = row[SGPMP_TAB_D11 + c];
     }
-    for (int k = tid; k < T * DP; k += BS) {
-        const int t = k / DP, j = k - t * DP;
-        mu[k] = j < d ? A.means[(size_t)bp * M + t * d + j] : (real)0;
-        bvec[k] = 0;
-    }
-    stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
+    for (int k = tid; k < T * DP; k += BS) { mu[k] = 0; bvec[k] = 0; }
+    __syncthreads();
+    for (int k = tid; k < M; k += BS) mu[(k / d) * DP + col(k % d)] = A.means[(size_t)bp * M + k];
+    stage_cta_constants<real, N, CHAIN, VOFF>(P, b, p / K, G, start, goal, sph);
     CostSmem<real> sm;
     sm.start = start; sm.goal = goal; sm.bvec = bvec; sm.sph = sph;
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
@@ -101,60 +115,143 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         // ---- b = Sigma^-1 mu (fp64 accumulate) ---------------------------------------------------------
         for (int k = tid; k < T * N; k += BS) {
             const int t = k / N, i = k - t * N;
-            precision_times_row<real, DP>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
+            precision_times_row<real, DP, VOFF>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + VOFF + i]);
         }
         if (last && A.means_pre)
-            for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[(k / d) * DP + (k % d)];
+            for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
         __syncthreads();
 
         // ---- pass 1: sample + cost, one thread per trajectory sample -----------------------------------
         const bool emit = last && A.samples != nullptr;
-        for (int s = tid; s < S; s += BS) {
-            TrajCost<real, N, CHAIN> tc;
-            tc.begin();
-            real yp[N], yv[N];
+        if constexpr (PACK == 2) {
+            // one sample per thread, DoF pairs packed (sgpmp_cost_pairs.cuh)
+            for (int s0 = tid; s0 < S; s0 += BS) {
+                TrajCostPairs<N, CHAIN> tc;
+                tc.begin();
+                F2 yp[NP2], yv[NP2], enp[NP2], env[NP2];
 #pragma unroll
-            for (int i = 0; i < N; ++i) { yp[i] = 0; yv[i] = 0; }
-            // One Philox call per DoF yields the normals of TWO time steps; the step body is kept as a single
-            // (not 2x unrolled) copy so that the hot loop stays inside the instruction cache.
-            real en[d];
+                for (int k = 0; k < NP2; ++k) yp[k] = yv[k] = f2(0.f, 0.f);
 #pragma unroll 1
-            for (int t = 0; t < T; ++t) {
-                real e[d];
-                if (eps) {
+                for (int t = 0; t < T; ++t) {
+                    F2 ep[NP2], ev[NP2];
+                    if (eps) {
 #pragma unroll
-                    for (int j = 0; j < d; ++j) e[j] = eps[((size_t)t * d + j) * S + s];
-                } else if ((t & 1) == 0) {
+                        for (int k = 0; k < NP2; ++k) {
+                            const int i0 = 2 * k, i1 = 2 * k + 1;
+                            const real* r0 = eps + ((size_t)t * d) * S + s0;
+                            ep[k] = f2(r0[(size_t)i0 * S], i1 < N ? r0[(size_t)i1 * S] : 0.f);
+                            ev[k] = f2(r0[(size_t)(N + i0) * S], i1 < N ? r0[(size_t)(N + i1) * S] : 0.f);
+                        }
+                    } else if ((t & 1) == 0) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s, pgid, e[i], e[N + i], en[i], en[N + i]);
-                } else {
+                        for (int k = 0; k < NP2; ++k) {
+                            float a0, a1, a2, a3, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                            normal4<float>(key, t >> 1, 2 * k, A.sample_gid0 + (uint32_t)s0, pgid, a0, a1, a2, a3);
+                            if (2 * k + 1 < N) normal4<float>(key, t >> 1, 2 * k + 1, A.sample_gid0 + (uint32_t)s0, pgid, b0, b1, b2, b3);
+                            ep[k] = f2(a0, b0); ev[k] = f2(a1, b1); enp[k] = f2(a2, b2); env[k] = f2(a3, b3);
+                        }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < d; ++j) e[j] = en[j];
+                        for (int k = 0; k < NP2; ++k) { ep[k] = enp[k]; ev[k] = env[k]; }
+                    }
+                    real r[8];
+                    load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
+                    load4(tabGH + t * 8 + 4, r[4], r[5], r[6], r[7]);
+                    const real* mrow = mu + t * DP;
+                    F2 xp[NP2], xv[NP2];
+#pragma unroll
+                    for (int k = 0; k < NP2; ++k) {
+                        const F2 np_ = vfma(r[0], ep[k], vneg(vfma(r[3], yp[k], r[4] * yv[k])));
+                        const F2 nv_ = vfma(r[1], ep[k], r[2] * ev[k]) - vfma(r[5], yp[k], r[6] * yv[k]);
+                        yp[k] = np_; yv[k] = nv_;
+                        xp[k] = f2(mrow[2 * k], mrow[2 * k + 1]) + np_;
+                        xv[k] = f2(mrow[VOFF + 2 * k], mrow[VOFF + 2 * k + 1]) + nv_;
+                    }
+                    tc.step(P, sm, t, T, xp, xv, bvec + t * DP);
+                    if (emit) {
+#pragma unroll
+                        for (int k = 0; k < NP2; ++k) {
+                            real* row = A.samples + ((size_t)bp * M + (size_t)t * d) * S + s0;
+                            row[(size_t)(2 * k) * S] = lane0(xp[k]);
+                            row[(size_t)(N + 2 * k) * S] = lane0(xv[k]);
+                            if (2 * k + 1 < N) { row[(size_t)(2 * k + 1) * S] = lane1(xp[k]); row[(size_t)(N + 2 * k + 1) * S] = lane1(xv[k]); }
+                        }
+                    }
                 }
-                real r[8], m[DP];
-                load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
-                load4(tabGH + t * 8 + 4, r[4], r[5], r[6], r[7]);
-#pragma unroll
-                for (int k = 0; k < DP / 4; ++k) load4(mu + t * DP + 4 * k, m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
-                real x[d];
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const real np_ = r[0] * e[i] - (r[3] * yp[i] + r[4] * yv[i]);
-                    const real nv_ = r[1] * e[i] + r[2] * e[N + i] - (r[5] * yp[i] + r[6] * yv[i]);
-                    yp[i] = np_; yv[i] = nv_;
-                    x[i] = m[i] + np_;
-                    x[N + i] = m[N + i] + nv_;
+                const real c = tc.total(P, sm, T, nullptr);
+                wsm[s0] = c;
+                if (last && A.costs) A.costs[(size_t)bp * S + s0] = c;
+            }
+        } else {
+            for (int k = tid; k * W < S; k += BS) {
+                const int s0 = k * W;                                   // lane 0 sample; lane 1 (packed) is s0 + 1
+                const int s1 = (W == 2 && s0 + 1 < S) ? s0 + 1 : s0;    // odd S: the last lane 1 shadows lane 0
+                TrajCost<V, N, CHAIN> tc;
+                tc.begin();
+                V yp[N], yv[N];
+    #pragma unroll
+                for (int i = 0; i < N; ++i) { yp[i] = vbroadcast<V>((real)0); yv[i] = vbroadcast<V>((real)0); }
+                // One Philox call per DoF (and lane) yields the normals of TWO time steps; the step body is kept as a
+                // single (not 2x unrolled) copy so that the hot loop stays inside the instruction cache.
+                V en[d];
+    #pragma unroll 1
+                for (int t = 0; t < T; ++t) {
+                    V e[d];
+                    if (eps) {
+    #pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            const real* row = eps + ((size_t)t * d + j) * S;
+                            if constexpr (W == 2) e[j] = f2(row[s0], row[s1]); else e[j] = row[s0];
+                        }
+                    } else if ((t & 1) == 0) {
+    #pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            if constexpr (W == 2) {
+                                float a0, a1, a2, a3, b0, b1, b2, b3;
+                                normal4<float>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s0, pgid, a0, a1, a2, a3);
+                                normal4<float>(key, t >> 1, i, A.sample_gid0 + (uint32_t)(s0 + 1), pgid, b0, b1, b2, b3);
+                                e[i] = f2(a0, b0); e[N + i] = f2(a1, b1); en[i] = f2(a2, b2); en[N + i] = f2(a3, b3);
+                            } else {
+                                normal4<real>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s0, pgid, e[i], e[N + i], en[i], en[N + i]);
+                            }
+                        }
+                    } else {
+    #pragma unroll
+                        for (int j = 0; j < d; ++j) e[j] = en[j];
+                    }
+                    real r[8], m[DP];
+                    load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
+                    load4(tabGH + t * 8 + 4, r[4], r[5], r[6], r[7]);
+    #pragma unroll
+                    for (int q = 0; q < DP / 4; ++q) load4(mu + t * DP + 4 * q, m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                    V x[d];
+    #pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const V np_ = vfma(r[0], e[i], vneg(vfma(r[3], yp[i], r[4] * yv[i])));
+                        const V nv_ = vfma(r[1], e[i], r[2] * e[N + i]) - vfma(r[5], yp[i], r[6] * yv[i]);
+                        yp[i] = np_; yv[i] = nv_;
+                        x[i] = m[i] + np_;
+                        x[N + i] = m[N + i] + nv_;
+                    }
+                    tc.step(P, sm, t, T, x, bvec + t * DP);
+                    if (emit) {
+    #pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            real* row = A.samples + ((size_t)bp * M + (size_t)t * d + j) * S;
+                            row[s0] = vlane(x[j], 0);
+                            if (W == 2 && s1 != s0) row[s1] = vlane(x[j], 1);
+                        }
+                    }
                 }
-                tc.step(P, sm, t, T, x, bvec + t * DP);
-                if (emit) {
-#pragma unroll
-                    for (int j = 0; j < d; ++j) A.samples[((size_t)bp * M + (size_t)t * d + j) * S + s] = x[j];
+                tc.finish(P, sm, T);
+                const V c = tc.total();
+                wsm[s0] = vlane(c, 0);
+                if (last && A.costs) A.costs[(size_t)bp * S + s0] = vlane(c, 0);
+                if (W == 2 && s1 != s0) {
+                    wsm[s1] = vlane(c, 1);
+                    if (last && A.costs) A.costs[(size_t)bp * S + s1] = vlane(c, 1);
                 }
             }
-            tc.finish(P, sm, T);
-            const real c = tc.total();
-            wsm[s] = c;
-            if (last && A.costs) A.costs[(size_t)bp * S + s] = c;
         }
         __syncthreads();
 
@@ -254,37 +351,54 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 acc[t * d + i] = gp_;
                 acc[t * d + N + i] = gv_;
                 mu[t * DP + i] += A.step * gp_;
-                mu[t * DP + N + i] += A.step * gv_;
+                mu[t * DP + VOFF + i] += A.step * gv_;
             }
         }
         __syncthreads();
         if (last && A.grad)
             for (int k = tid; k < M; k += BS) A.grad[(size_t)bp * M + k] = acc[k];
     }
-    for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[(k / d) * DP + (k % d)];
+    for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
 }
 
-template <typename real, int N, int BS, int CHAIN>
+template <typename real, int PACK, int N, int BS, int CHAIN>
 static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
-    const int d = 2 * N, M = sh.T * d, DP = (d + 3) & ~3;
+    const int d = 2 * N, M = sh.T * d, VOFF = (PACK == 2) ? 2 * ((N + 1) / 2) : N, DP = (PACK == 2) ? 2 * VOFF : ((d + 3) & ~3);
     const size_t smem = (size_t)sh.T * 7 * sizeof(double) +
-                        ((size_t)sh.T * (8 + 2 * DP) + (size_t)M + sh.S + 4 * BS + 32 + 2 * d + SPH_SMEM) * sizeof(real);
+                        ((size_t)sh.T * (8 + 2 * DP) + (size_t)M + sh.S + 4 * BS + 32 + 4 * VOFF + SPH_SMEM) * sizeof(real);
     if (smem > 227 * 1024) {
         set_error("sgpmp_iterate: T=%d, S=%d need %zu bytes of shared memory (> 227 KiB)", sh.T, sh.S, smem);
         return SGPMP_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(iterate_kernel<real, N, BS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    iterate_kernel<real, N, BS, CHAIN><<<(unsigned)(sh.B * sh.G * sh.K), BS, smem, st>>>(P, A);
+        cudaFuncSetAttribute(iterate_kernel<real, PACK, N, BS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    iterate_kernel<real, PACK, N, BS, CHAIN><<<(unsigned)(sh.B * sh.G * sh.K), BS, smem, st>>>(P, A);
     SGPMP_CHECK_LAUNCH("sgpmp_iterate");
     return SGPMP_OK;
 }
 
 template <typename real, int N, int CHAIN>
 static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
-    static const char* force_bs = getenv("SGPMP_ITERATE_BS");   // tuning aid
-    if (sh.S > 128 && !(force_bs && atoi(force_bs) == 128)) return launch_iterate_nb<real, N, 256, CHAIN>(sh, P, A, st);
-    return launch_iterate_nb<real, N, 128, CHAIN>(sh, P, A, st);
+    static const char* force_bs = getenv("SGPMP_ITERATE_BS");       // tuning aids
+    static const char* pack_env = getenv("SGPMP_ITERATE_PACK");     // 0 scalar, 2 dof pairs (default)
+    const bool bs128 = force_bs && atoi(force_bs) == 128;
+    if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
+        const int pack = pack_env ? atoi(pack_env) : 2;
+        // dof-pair packing covers the occupancy-map field and the Panda structure; generic FK chains stay scalar
+        const bool pairs_ok = (CHAIN >= 1) || !(P.has_spheres || P.has_self);
+        if (pack == 2 && pairs_ok) {
+            if (sh.S > 128 && !bs128) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
+            return launch_iterate_nb<real, 2, N, 128, CHAIN>(sh, P, A, st);
+        }
+#ifdef SGPMP_ENABLE_TWO_SAMPLE_PACKING   // measured 4 % slower than dof pairs (register pressure); kept for experiments
+        if (pack == 1) {
+            if (sh.S > 256 && !bs128) return launch_iterate_nb<real, 1, N, 256, CHAIN>(sh, P, A, st);
+            return launch_iterate_nb<real, 1, N, 128, CHAIN>(sh, P, A, st);
+        }
+#endif
+    }
+    if (sh.S > 128 && !bs128) return launch_iterate_nb<real, 0, N, 256, CHAIN>(sh, P, A, st);
+    return launch_iterate_nb<real, 0, N, 128, CHAIN>(sh, P, A, st);
 }
 
 template <typename real>

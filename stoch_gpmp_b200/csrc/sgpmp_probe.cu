@@ -37,18 +37,70 @@ __global__ void __launch_bounds__(256) probe_mufu_kernel(int iters, float seed, 
     if (r == 123.456f) out[0] = r;
 }
 
+__device__ __forceinline__ unsigned long long ffma2_raw(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// Packed-FP32 / issue-port experiments (64 "FP slots" per thread per iteration):
+//   mode 2: 64 FFMA2 (packed fp32x2: 128 FMA)              mode 5: 128 FFMA (same FP work, scalar)
+//   mode 3: 128 FFMA + 64 independent LOP3                 mode 4: 64 FFMA2 + 64 independent LOP3
+// If FFMA2 frees issue slots, mode 4 runs in the time of mode 2 while mode 3 needs 1.5x mode 5.
+template <int mode>
+__global__ void __launch_bounds__(256) probe_mix_kernel(int iters, float seed, float* __restrict__ out) {
+    float2 f[8];
+    unsigned u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f[k] = make_float2(seed + threadIdx.x + k, seed - k); u[k] = threadIdx.x * 2654435761u + k; }
+    const float2 m = make_float2(0.999f, 0.998f), c = make_float2(1e-3f, 2e-3f);
+    const unsigned long long mm = *reinterpret_cast<const unsigned long long*>(&m), cc = *reinterpret_cast<const unsigned long long*>(&c);
+    const unsigned ka = 0x9E3779B9u + threadIdx.x, kb = 0x85EBCA6Bu;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (mode == 2 || mode == 4) {
+                    unsigned long long v = *reinterpret_cast<unsigned long long*>(&f[k]);
+                    v = ffma2_raw(v, mm, cc);
+                    f[k] = *reinterpret_cast<float2*>(&v);
+                } else {
+                    f[k].x = fmaf(f[k].x, m.x, c.x);
+                    f[k].y = fmaf(f[k].y, m.y, c.y);
+                }
+                if (mode == 3 || mode == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[k]) : "r"(ka), "r"(kb));
+            }
+        }
+    }
+    float r = 0;
+    unsigned q = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { r += f[k].x + f[k].y; q ^= u[k]; }
+    if (r == 123.456f || q == 0x12345u) out[0] = r + q;
+}
+
 }  // namespace sgpmp
 
 using namespace sgpmp;
 
 /* mode 0: FP32 FMA (2 flop each; launches `blocks` x 256 threads, 128 FMA per thread per iteration);
- * mode 1: MUFU ex2 (64 per thread per iteration). */
+ * mode 1: MUFU ex2 (64 per thread per iteration);
+ * modes 2-4: packed-FP32 / mixed-issue experiments (64 FP instructions per thread per iteration, see probe_mix_kernel). */
 extern "C" int sgpmp_probe(int32_t mode, int32_t blocks, int32_t iters, void* scratch, void* stream) {
     SGPMP_REQUIRE(blocks > 0 && iters > 0 && scratch, "sgpmp_probe: bad arguments");
     if (mode == 0)
         probe_fma_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)scratch);
-    else
+    else if (mode == 1)
         probe_mufu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, (float*)scratch);
+    else if (mode == 2)
+        probe_mix_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)scratch);   // 64 FP instr / thread / iter
+    else if (mode == 3)
+        probe_mix_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)scratch);
+    else if (mode == 4)
+        probe_mix_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)scratch);
+    else
+        probe_mix_kernel<5><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, (float*)scratch);
     SGPMP_CHECK_LAUNCH("sgpmp_probe");
     return SGPMP_OK;
 }

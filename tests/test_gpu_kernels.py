@@ -372,8 +372,10 @@ def test_fused_equals_separate_kernels_inkernel_rng(case, dtype, cuda):
     mu0 += 0.01 * torch.arange(B, device=cuda, dtype=dtype).view(B, 1, 1, 1)
     # The loop is chaotic in fp32 (a mean perturbation d changes the logits by ~|dc/dmu| d / tau ~ 200 d here), so
     # the two paths are compared iteration by iteration from the SAME means; fp64 also checks the 3-iteration chain.
-    tol = 2e-5 if dtype == torch.float32 else 1e-9
-    wtol = 5e-4 if dtype == torch.float32 else 1e-8
+    # fp32: the fused kernel sums per-DoF-pair partial costs (packed FP32), K3 sums serially: 4e-5 apart on costs of
+    # ~6e4 that cancel from larger terms; both are within 1e-5 of the fp64 oracle on the golden cases.
+    tol = 1e-4 if dtype == torch.float32 else 1e-9
+    wtol = 2e-3 if dtype == torch.float32 else 1e-8
     mu_s = mu0.clone()
     for it in range(3):
         pre_means = mu_s.clone()
@@ -383,7 +385,7 @@ def test_fused_equals_separate_kernels_inkernel_rng(case, dtype, cuda):
         c = _ops().cost(sh, desc, tab, xs, mu_s)
         grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], c, xs, mu_s)
         assert torch.equal(out['means_pre'], pre_means)
-        assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < tol
+        assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < (2e-6 if dtype == torch.float32 else tol)
         assert float((out['costs'] - c).abs().max() / c.abs().max()) < tol
         assert float((out['weights'] - w).abs().max()) < wtol
         assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < 10 * wtol
@@ -462,7 +464,7 @@ def test_fused_full_size_properties(cuda):
     assert torch.equal(mu1, mu2)
     assert float((o1['weights'].sum(-1) - 1).abs().max()) < 1e-5
     c3 = _ops().cost(sh, low.desc(1.0, sp), tab, o1['samples'], mu0)
-    assert float((c3 - o1['costs']).abs().max() / c3.abs().max()) < 1e-6
+    assert float((c3 - o1['costs']).abs().max() / c3.abs().max()) < 1e-5
     mu_k4 = mu0.clone()
     grad, w = _ops().update(sh, 1.0, 0.1, o1['costs'], o1['samples'], mu_k4)
     assert float((w - o1['weights']).abs().max()) < 1e-6
