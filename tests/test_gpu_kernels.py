@@ -496,3 +496,39 @@ def test_split_particle_stats_equal_single_update(cuda):
     assert rel(grad.cpu().numpy(), grad_ref.cpu().numpy()) < 1e-9
     assert rel(mu_split.cpu().numpy(), mu_ref.cpu().numpy()) < 1e-12
     assert rel(mu_split.cpu().numpy()[0], g['it0_means_post']) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("n,T,S,G,K", [(2, 7, 33, 1, 3), (3, 9, 5, 2, 1), (4, 6, 130, 1, 1), (6, 5, 17, 2, 2), (7, 11, 257, 1, 1)])
+def test_fused_ragged_shapes_equal_separate_kernels(n, T, S, G, K, dtype, cuda):
+    """Edge shapes through the fused loop — odd T (half-used last Philox pair), odd S, S not a multiple of the
+    block size, one sample chunk more than a block, every instantiated DoF count (odd n exercises the ghost DoF
+    of the packed kernel), a single goal — against K2 -> K3 -> K4 with the same draw index."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, CostGoalPrior
+    B = 2
+    d = 2 * n
+    ta = dict(device=cuda, dtype=dtype)
+    rs = np.random.RandomState(n * 100 + T)
+    spec = dict(T=T, dt=0.1, goals=np.zeros((G, d)), sigma_start_sample=0.3, sigma_gp_sample=1.0, sigma_goal_sample=0.3)
+    tab = _tables(spec, cuda)
+    start = torch.tensor(rs.uniform(-0.3, 0.3, (B, d)), **ta)
+    goals = torch.tensor(rs.uniform(-0.5, 0.5, (B, G, d)), **ta)
+    comp = CostComposite(n, T, [CostGP(n, T, start, 0.1, dict(sigma_start=0.5, sigma_gp=2.0), ta),
+                                CostGoalPrior(n, T, multi_goal_states=goals, num_particles_per_goal=K, num_samples=S,
+                                              sigma_goal_prior=1.0, tensor_args=ta)], tensor_args=ta)
+    low = comp.lower(B, G, cuda, dtype)
+    desc = low.desc(20.0, None)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype, problem_gid0=3)
+    mu0 = torch.tensor(rs.uniform(-0.5, 0.5, (B, G * K, T, d)), **ta)
+    mu_f, mu_s = mu0.clone(), mu0.clone()
+    out = _ops().iterate(sh, desc, tab, 0.5, 1, mu_f, seed=17, draw0=2, want_samples=True)
+    xs = _ops().sample(sh, tab, mu_s, seed=17, draw=2)
+    c = _ops().cost(sh, desc, tab, xs, mu_s)
+    grad, w = _ops().update(sh, 20.0, 0.5, c, xs, mu_s)
+    f32 = dtype == torch.float32
+    assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < (2e-6 if f32 else 1e-12)
+    assert float((out['costs'] - c).abs().max() / c.abs().max()) < (2e-5 if f32 else 1e-11)
+    assert float((out['weights'] - w).abs().max()) < (1e-4 if f32 else 1e-10)
+    assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < (1e-3 if f32 else 1e-9)
+    assert float((mu_f - mu_s).abs().max() / mu_s.abs().max()) < (1e-4 if f32 else 1e-10)
+    assert float((out['weights'].sum(-1) - 1).abs().max()) < 1e-5
