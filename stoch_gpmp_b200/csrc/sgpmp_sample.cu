@@ -67,9 +67,89 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sampl
     }
 }
 
+// In-kernel-RNG variant for the instantiated DoF counts: one thread per SAMPLE with all DoFs in registers (the
+// mapping of the fused kernel's pass 1).  The generic kernel above spends 44 k instructions per trajectory sample
+// (per-thread index arithmetic for one DoF); this one ~23 k, which moves the kernel from 35 % to >60 % of the HBM
+// write roofline.  Row (t, j) of the S-minor output is written by consecutive threads: fully coalesced.
+template <typename real, int N>
+__global__ void __launch_bounds__(128)
+sample_rng_kernel(int S, int T, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
+                  const real* __restrict__ means, RngKey key, real* __restrict__ samples, real* __restrict__ eps_out) {
+    constexpr int d = 2 * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* gh = reinterpret_cast<real*>(smem_raw);   // [T][8]
+    real* mu = gh + (size_t)T * 8;                  // [T][d]
+    const int bp = blockIdx.x;
+    for (int k = threadIdx.x; k < T * 8; k += blockDim.x) gh[k] = (k & 7) < 7 ? (real)tab[(size_t)(k >> 3) * SGPMP_TABLE_STRIDE + (k & 7)] : (real)0;
+    for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
+    __syncthreads();
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
+    real* out = samples + (size_t)bp * T * d * S + s;
+    real* eo = eps_out ? eps_out + (size_t)bp * T * d * S + s : nullptr;
+    real yp[N], yv[N], en[d];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { yp[i] = 0; yv[i] = 0; }
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        real e[d];
+        if ((t & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, sample_gid0 + (uint32_t)s, pgid, e[i], e[N + i], en[i], en[N + i]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < d; ++j) e[j] = en[j];
+        }
+        const real* r = gh + t * 8;
+        const real* m = mu + t * d;
+        real* row = out + (size_t)t * d * S;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const real np_ = r[0] * e[i] - (r[3] * yp[i] + r[4] * yv[i]);
+            const real nv_ = r[1] * e[i] + r[2] * e[N + i] - (r[5] * yp[i] + r[6] * yv[i]);
+            yp[i] = np_; yv[i] = nv_;
+            row[(size_t)i * S] = m[i] + np_;
+            row[(size_t)(N + i) * S] = m[N + i] + nv_;
+        }
+        if (eo) {
+            real* er = eo + (size_t)t * d * S;
+#pragma unroll
+            for (int j = 0; j < d; ++j) er[(size_t)j * S] = e[j];
+        }
+    }
+}
+
+template <typename real, int N>
+static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, const void* means, uint64_t seed, uint32_t draw,
+                             void* samples, void* eps_out, cudaStream_t st) {
+    const int NP = sh.G * sh.K, bs = 128;
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
+    const size_t smem = (size_t)sh.T * (8 + 2 * N) * sizeof(real);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) return SGPMP_ERR_UNSUPPORTED;      // caller falls back to the generic kernel
+        cudaFuncSetAttribute(sample_rng_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
+    sample_rng_kernel<real, N><<<grid, bs, smem, st>>>(sh.S, sh.T, sh.problem_gid0 * NP, (uint32_t)sh.sample_gid0, tables,
+                                                       (const real*)means, key, (real*)samples, (real*)eps_out);
+    SGPMP_CHECK_LAUNCH("sgpmp_sample");
+    return SGPMP_OK;
+}
+
 template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
                          uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st) {
+    if (!eps_in) {      // in-kernel RNG: thread-per-sample kernel for the instantiated DoF counts
+        int rc = SGPMP_ERR_UNSUPPORTED;
+        switch (sh.n_dof) {
+#define SGPMP_DOF_CASE(N) case N: rc = launch_sample_rng<real, N>(sh, tables, means, seed, draw, samples, eps_out, st); break;
+#include "sgpmp_dof_list.inc"
+#undef SGPMP_DOF_CASE
+            default: break;
+        }
+        if (rc != SGPMP_ERR_UNSUPPORTED) return rc;
+    }
     const int NP = sh.G * sh.K;
     const int bs = 256;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S * sh.n_dof + bs - 1) / bs));
