@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGPMP_ABI_VERSION 2
+#define SGPMP_ABI_VERSION 3
 
 enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
 
@@ -120,6 +120,11 @@ typedef struct sgpmp_cost_desc {
      * pairs of link frames incl. i == j, weight 1/self_sigma_coll^2 */
     double self_margin;              /* <= 0: absent */
     double self_sigma_coll;
+
+    /* optional byte copy of occ_map ([n_maps, map_h, map_w] uint8, same values: occupancy COUNTS are small
+     * integers, envs/obst_map.py:71,104).  When non-NULL the kernels gather from it instead of occ_map: a 200x200
+     * map is 40 KB instead of 160 KB (fp32), so it stays L1-resident.  Bit-exact: every count <= 255 is exact in fp32/fp64. */
+    const uint8_t* occ_map_u8;
 } sgpmp_cost_desc_t;
 
 int sgpmp_abi_version(void);

@@ -14,7 +14,7 @@ MAX_FRAMES = 16
 MAX_SPHERES = 16
 NUM_TERMS = 6
 TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Shape(C.Structure):
@@ -37,6 +37,7 @@ class CostDesc(C.Structure):
         ("chain_R", (C.c_double * 9) * MAX_FRAMES), ("chain_p", (C.c_double * 3) * MAX_FRAMES),
         ("chain_joint", C.c_int32 * MAX_FRAMES),
         ("self_margin", C.c_double), ("self_sigma_coll", C.c_double),
+        ("occ_map_u8", C.c_void_p),
     ]
 
 

@@ -45,6 +45,7 @@ struct CostParams {
     const real* goals;     // [B,G,d] or null
     // map
     const real* occ_map;
+    const uint8_t* occ_map_u8;   // optional byte copy of occ_map (gathered instead of it when non-null)
     const int32_t* map_of_problem;
     int32_t map_h, map_w, origin_xi, origin_yi, n_maps;
     real map_inv_cell, map_origin_x, map_origin_y, map_w_coll;  // w_coll = 1/sigma_coll^2

@@ -44,6 +44,7 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
         }
         if (sh.n_dof < 2) { set_error("cost desc: occupancy map needs n_dof >= 2"); return SGPMP_ERR_INVALID_ARG; }
         o.occ_map = (const real*)d.occ_map;
+        o.occ_map_u8 = d.occ_map_u8;
         o.map_of_problem = d.map_of_problem;
         o.map_h = d.map_h; o.map_w = d.map_w; o.n_maps = d.n_maps;
         o.origin_xi = d.origin_xi; o.origin_yi = d.origin_yi;
@@ -133,6 +134,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+    sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
 
     TrajCost<real, N, CHAIN> tc;
     tc.begin();

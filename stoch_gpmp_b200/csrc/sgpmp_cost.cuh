@@ -31,6 +31,7 @@ struct CostSmem {
     const real* sph;     // [O][8]   (cx, cy, cz, k, ax, ay, az, b): k = -0.5/r^2 (* log2 e in fp32),
                          //          a = -2 k c, b = k |c|^2  so that  k |p - c|^2 = k |p|^2 + a.p + b
     const real* map;     // occupancy map of this problem (global memory)
+    const uint8_t* map_u8;   // byte copy of it, or null
     real coll_const;     // RBF sum of the link frames whose position does not depend on q (structured chains)
     real self_const;     // q-independent part of the self-collision sum (structured chains)
 };
@@ -280,6 +281,7 @@ struct TrajCost {
         int ix = (int)sg_floor(xo), iy = (int)sg_floor(yo);
         ix = min(max(ix, 0), P.map_h - 1);
         iy = min(max(iy, 0), P.map_w - 1);
+        if (sm.map_u8) return (real)__ldg(sm.map_u8 + (size_t)iy * P.map_w + ix);
         return __ldg(sm.map + (size_t)iy * P.map_w + ix);
     }
     __device__ __forceinline__ V map_value(const CostParams<real>& P, const CostSmem<real>& sm, V x, V y) const {

@@ -121,6 +121,7 @@ struct TrajCostPairs {
         int ix = (int)floorf(xo), iy = (int)floorf(yo);
         ix = min(max(ix, 0), P.map_h - 1);
         iy = min(max(iy, 0), P.map_w - 1);
+        if (sm.map_u8) return (float)__ldg(sm.map_u8 + (size_t)iy * P.map_w + ix);
         return __ldg(sm.map + (size_t)iy * P.map_w + ix);
     }
 

@@ -104,6 +104,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+    sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     __syncthreads();
 
     for (int it = 0; it < A.n_iters; ++it) {
