@@ -76,14 +76,24 @@ update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs,
         for (int s = threadIdx.x; s < S; s += blockDim.x) weights[bp * S + s] = wsm[s];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const real* xs = samples + bp * (size_t)M * S;
-    for (int r = warp; r < M; r += nw) {
-        const real mu = means[bp * M + r];
-        real acc = 0;
-        for (int s = lane; s < S; s += 32) acc += wsm[s] * (xs[(size_t)r * S + s] - mu);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            if (grad) grad[bp * M + r] = acc;
-            means[bp * M + r] = mu + step * acc;
+    // four rows per warp pass: four independent load streams in flight (the kernel is HBM-latency bound otherwise)
+    for (int r0 = warp * 4; r0 < M; r0 += nw * 4) {
+        real acc[4] = {0, 0, 0, 0}, mu[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mu[q] = (r0 + q < M) ? means[bp * M + r0 + q] : (real)0;
+        for (int s = lane; s < S; s += 32) {
+            const real w = wsm[s];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (r0 + q < M) acc[q] += w * (xs[(size_t)(r0 + q) * S + s] - mu[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const real a = warp_sum(acc[q]);
+            if (lane == 0 && r0 + q < M) {
+                if (grad) grad[bp * M + r0 + q] = a;
+                means[bp * M + r0 + q] = mu[q] + step * a;
+            }
         }
     }
 }
