@@ -16,6 +16,7 @@
 //     banded recurrence per DoF applies L.  mu and b = Sigma^-1 mu stay in shared memory across
 //     iterations; particles are independent, so no grid-wide synchronisation exists anywhere.
 //   * FP32-pipe/MUFU bound; HBM traffic is O(NP*M) per iteration instead of 3*M*S*NP.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "sgpmp_common.cuh"
@@ -32,6 +33,8 @@
 #ifndef SGPMP_MINB_PACKED
 #define SGPMP_MINB_PACKED 2
 #endif
+
+namespace cg = cooperative_groups;
 
 namespace sgpmp {
 
@@ -58,8 +61,13 @@ struct IterArgs {
 template <typename real, int PACK> struct PackV { using type = real; };
 template <> struct PackV<float, 1> { using type = F2; };
 
-template <typename real, int PACK, int N, int BS, int CHAIN>
-__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (PACK == 1 ? SGPMP_MINB_PACKED : (BS == 128 ? SGPMP_MINB128 : SGPMP_MINB256)) : 1))
+// CL > 1: one particle's S samples are split over a thread-block CLUSTER of CL CTAs (low-latency mode for few
+// problems: B*NP CTAs cannot fill 148 SMs).  Each CTA draws and scores samples [cr*S/CL, (cr+1)*S/CL) with the same
+// global RNG counters; the softmax statistics (max, sum) and the weighted eps-sum are exchanged through distributed
+// shared memory (cluster.map_shared_rank) with four cluster barriers per iteration, then every CTA applies the
+// identical update to its own copy of mu.  No global memory or extra launch is involved.
+template <typename real, int PACK, int N, int BS, int CHAIN, int CL>
+__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (PACK == 1 ? SGPMP_MINB_PACKED : (BS == 256 ? SGPMP_MINB256 : SGPMP_MINB128)) : 1))
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
     using V = typename PackV<real, PACK>::type;
     constexpr int W = VT<V>::W;
@@ -78,14 +86,19 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     real* bvec = mu + (size_t)T * DP;                         // [T][DP]
     double* tabDO = reinterpret_cast<double*>(bvec + (size_t)T * DP);   // [T][7]
     real* acc = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]  sum_s w_s eps_s, then grad
-    real* wsm = acc + M;                                      // [S]
-    real* part = wsm + S;                                     // [4*BS] partial sums of pass 2
+    real* wsm = acc + M;                                      // [ceil(S/CL)] costs -> weights of this CTA's samples
+    real* part = wsm + (S + CL - 1) / CL;                     // [4*BS] partial sums of pass 2
     real* red = part + 4 * BS;                                // [32]
     real* start = red + 32;                                   // [2*VOFF]
     real* goal = start + 2 * VOFF;                            // [2*VOFF]
+    real* xch = goal + 2 * VOFF;                              // [4]   cluster exchange: local max, local sum
+    real* accsum = xch + 4;                                   // [T][d] cluster-reduced eps-sum (CL > 1 only)
 
     const int NP = G * K;
-    const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
+    const int bp = blockIdx.x / CL, cr = blockIdx.x % CL, b = bp / NP, p = bp - b * NP;
+    const int n_particles = gridDim.x / CL;
+    const int S_loc = (S + CL - 1) / CL;
+    const int s_lo = cr * S_loc, s_hi = min(S, s_lo + S_loc), ns = max(0, s_hi - s_lo);   // this CTA's samples
     const int tid = threadIdx.x;
     const uint32_t pgid = A.particle_gid0 + (uint32_t)bp;
 
@@ -111,14 +124,14 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         const bool last = (it == A.n_iters - 1);
         RngKey key = A.key;
         key.draw += (uint32_t)it;
-        const real* eps = A.eps_in ? A.eps_in + ((size_t)it * gridDim.x + bp) * (size_t)M * S : nullptr;
+        const real* eps = A.eps_in ? A.eps_in + ((size_t)it * n_particles + bp) * (size_t)M * S : nullptr;
 
         // ---- b = Sigma^-1 mu (fp64 accumulate) ---------------------------------------------------------
         for (int k = tid; k < T * N; k += BS) {
             const int t = k / N, i = k - t * N;
             precision_times_row<real, DP, VOFF>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + VOFF + i]);
         }
-        if (last && A.means_pre)
+        if (last && A.means_pre && cr == 0)
             for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
         __syncthreads();
 
@@ -126,7 +139,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         const bool emit = last && A.samples != nullptr;
         if constexpr (PACK == 2) {
             // one sample per thread, DoF pairs packed (sgpmp_cost_pairs.cuh)
-            for (int s0 = tid; s0 < S; s0 += BS) {
+            for (int s0 = s_lo + tid; s0 < s_hi; s0 += BS) {
                 TrajCostPairs<N, CHAIN> tc;
                 tc.begin();
                 F2 yp[NP2], yv[NP2], enp[NP2], env[NP2];
@@ -180,13 +193,13 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                     }
                 }
                 const real c = tc.total(P, sm, T, nullptr);
-                wsm[s0] = c;
+                wsm[s0 - s_lo] = c;
                 if (last && A.costs) A.costs[(size_t)bp * S + s0] = c;
             }
         } else {
-            for (int k = tid; k * W < S; k += BS) {
-                const int s0 = k * W;                                   // lane 0 sample; lane 1 (packed) is s0 + 1
-                const int s1 = (W == 2 && s0 + 1 < S) ? s0 + 1 : s0;    // odd S: the last lane 1 shadows lane 0
+            for (int k = tid; s_lo + k * W < s_hi; k += BS) {
+                const int s0 = s_lo + k * W;                               // lane 0 sample; lane 1 (packed) is s0 + 1
+                const int s1 = (W == 2 && s0 + 1 < s_hi) ? s0 + 1 : s0;    // odd count: the last lane 1 shadows lane 0
                 TrajCost<V, N, CHAIN> tc;
                 tc.begin();
                 V yp[N], yv[N];
@@ -246,20 +259,20 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 }
                 tc.finish(P, sm, T);
                 const V c = tc.total();
-                wsm[s0] = vlane(c, 0);
+                wsm[s0 - s_lo] = vlane(c, 0);
                 if (last && A.costs) A.costs[(size_t)bp * S + s0] = vlane(c, 0);
                 if (W == 2 && s1 != s0) {
-                    wsm[s1] = vlane(c, 1);
+                    wsm[s1 - s_lo] = vlane(c, 1);
                     if (last && A.costs) A.costs[(size_t)bp * S + s1] = vlane(c, 1);
                 }
             }
         }
         __syncthreads();
 
-        // ---- softmax over the S samples of this particle ------------------------------------------------
+        // ---- softmax over the S samples of this particle (cluster-wide when CL > 1) ----------------------
         {
             real m = -INFINITY;
-            for (int s = tid; s < S; s += BS) {
+            for (int s = tid; s < ns; s += BS) {
                 const real z = -wsm[s] / P.temperature;
                 wsm[s] = z;
                 m = sg_max(m, z);
@@ -269,9 +282,15 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             __syncthreads();
             m = red[0];
             for (int k = 1; k < BS / 32; ++k) m = sg_max(m, red[k]);
+            if constexpr (CL > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+                if (tid == 0) xch[0] = m;
+                cluster.sync();
+                for (int r = 0; r < CL; ++r) m = sg_max(m, *cluster.map_shared_rank(xch, r));
+            }
             __syncthreads();
             real Z = 0;
-            for (int s = tid; s < S; s += BS) {
+            for (int s = tid; s < ns; s += BS) {
                 const real ex = sg_exp(wsm[s] - m);
                 wsm[s] = ex;
                 Z += ex;
@@ -281,10 +300,17 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             __syncthreads();
             Z = 0;
             for (int k = 0; k < BS / 32; ++k) Z += red[k];
-            for (int s = tid; s < S; s += BS) {
+            if constexpr (CL > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+                if (tid == 0) xch[1] = Z;
+                cluster.sync();
+                Z = 0;
+                for (int r = 0; r < CL; ++r) Z += *cluster.map_shared_rank(xch + 1, r);     // fixed rank order: identical on every CTA
+            }
+            for (int s = tid; s < ns; s += BS) {
                 const real w = wsm[s] / Z;
                 wsm[s] = w;
-                if (last && A.weights) A.weights[(size_t)bp * S + s] = w;
+                if (last && A.weights) A.weights[(size_t)bp * S + s_lo + s] = w;
             }
             __syncthreads();
         }
@@ -294,7 +320,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             const int warp = tid >> 5, lane = tid & 31;
             for (int r = warp; r < M; r += BS / 32) {
                 real a = 0;
-                for (int s = lane; s < S; s += 32) a += wsm[s] * eps[(size_t)r * S + s];
+                for (int s = lane; s < ns; s += 32) a += wsm[s] * eps[(size_t)r * S + s_lo + s];
                 a = warp_sum(a);
                 if (lane == 0) acc[r] = a;
             }
@@ -308,11 +334,11 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 const int tp = item / N, i = item - tp * N;
                 if (active) {
-                    for (int s = split; s < S; s += nsplit) {
+                    for (int s = split; s < ns; s += nsplit) {
                         const real w = wsm[s];
                         if (w == (real)0) continue;
                         real p0, v0, p1, v1;
-                        normal4<real>(key, tp, i, A.sample_gid0 + (uint32_t)s, pgid, p0, v0, p1, v1);
+                        normal4<real>(key, tp, i, A.sample_gid0 + (uint32_t)(s_lo + s), pgid, p0, v0, p1, v1);
                         a0 += w * p0; a1 += w * v0; a2 += w * p1; a3 += w * v1;
                     }
                 }
@@ -338,6 +364,19 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             }
         }
         __syncthreads();
+        if constexpr (CL > 1) {
+            // all-reduce of the partial eps-sums over the cluster through distributed shared memory
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            for (int k = tid; k < M; k += BS) {
+                real a = 0;
+                for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(acc, r)[k];
+                accsum[k] = a;
+            }
+            cluster.sync();                       // every CTA has read every partial before acc is reused
+            for (int k = tid; k < M; k += BS) acc[k] = accsum[k];
+            __syncthreads();
+        }
 
         // ---- grad = L acc (banded recurrence, one thread per DoF); mu += step * grad --------------------
         if (tid < N) {
@@ -356,24 +395,43 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             }
         }
         __syncthreads();
-        if (last && A.grad)
+        if (last && A.grad && cr == 0)
             for (int k = tid; k < M; k += BS) A.grad[(size_t)bp * M + k] = acc[k];
     }
-    for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
+    if (cr == 0)
+        for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
 }
 
-template <typename real, int PACK, int N, int BS, int CHAIN>
+template <typename real, int PACK, int N, int BS, int CHAIN, int CL = 1>
 static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
     const int d = 2 * N, M = sh.T * d, VOFF = (PACK == 2) ? 2 * ((N + 1) / 2) : N, DP = (PACK == 2) ? 2 * VOFF : ((d + 3) & ~3);
+    const int S_loc = (sh.S + CL - 1) / CL;
     const size_t smem = (size_t)sh.T * 7 * sizeof(double) +
-                        ((size_t)sh.T * (8 + 2 * DP) + (size_t)M + sh.S + 4 * BS + 32 + 4 * VOFF + SPH_SMEM) * sizeof(real);
+                        ((size_t)sh.T * (8 + 2 * DP) + (size_t)M * (CL > 1 ? 2 : 1) + S_loc + 4 * BS + 32 + 4 * VOFF + 4 + SPH_SMEM) * sizeof(real);
     if (smem > 227 * 1024) {
         set_error("sgpmp_iterate: T=%d, S=%d need %zu bytes of shared memory (> 227 KiB)", sh.T, sh.S, smem);
         return SGPMP_ERR_UNSUPPORTED;
     }
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(iterate_kernel<real, PACK, N, BS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    iterate_kernel<real, PACK, N, BS, CHAIN><<<(unsigned)(sh.B * sh.G * sh.K), BS, smem, st>>>(P, A);
+    auto kern = iterate_kernel<real, PACK, N, BS, CHAIN, CL>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned n_cta = (unsigned)(sh.B * sh.G * sh.K) * CL;
+    if constexpr (CL > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_cta);
+        cfg.blockDim = dim3(BS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, P, A);
+    } else {
+        kern<<<n_cta, BS, smem, st>>>(P, A);
+    }
     SGPMP_CHECK_LAUNCH("sgpmp_iterate");
     return SGPMP_OK;
 }
@@ -383,6 +441,13 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
     static const char* force_bs = getenv("SGPMP_ITERATE_BS");       // tuning aids
     static const char* pack_env = getenv("SGPMP_ITERATE_PACK");     // 0 scalar, 2 dof pairs (default)
     const bool bs128 = force_bs && atoi(force_bs) == 128;
+    // few problems: split every particle's samples over a cluster of 8 CTAs (DSMEM reductions) to use more SMs
+    static const char* cl_env = getenv("SGPMP_ITERATE_CLUSTER");    // 0 disables
+    const bool want_cluster = !(cl_env && atoi(cl_env) == 0) && !A.eps_in && sh.S >= 256 && (long)sh.B * sh.G * sh.K * 8 <= 2 * 148;
+    if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
+        const bool pairs_ok_c = (CHAIN >= 1) || !(P.has_spheres || P.has_self);
+        if (want_cluster && pairs_ok_c) return launch_iterate_nb<real, 2, N, 64, CHAIN, 8>(sh, P, A, st);
+    }
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const int pack = pack_env ? atoi(pack_env) : 2;
         // dof-pair packing covers the occupancy-map field and the Panda structure; generic FK chains stay scalar

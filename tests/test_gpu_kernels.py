@@ -532,3 +532,48 @@ def test_fused_ragged_shapes_equal_separate_kernels(n, T, S, G, K, dtype, cuda):
     assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < (1e-3 if f32 else 1e-9)
     assert float((mu_f - mu_s).abs().max() / mu_s.abs().max()) < (1e-4 if f32 else 1e-10)
     assert float((out['weights'].sum(-1) - 1).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("n,S", [(2, 512), (7, 256), (7, 300)])
+def test_cluster_mode_equals_separate_kernels(n, S, cuda):
+    """Few problems (B*NP*8 <= 296 CTAs) with S >= 256 run the fused loop in thread-block-CLUSTER mode: a particle's
+    samples are split over 8 CTAs and the softmax / weighted-sum reductions go through distributed shared memory.
+    The result must equal K2 -> K3 -> K4 (no clusters) on the same draw; S=300 leaves ragged per-CTA slices."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, CostGoalPrior
+    dtype = torch.float32
+    B, G, K, T = 1, 3, 1, 16
+    d = 2 * n
+    ta = dict(device=cuda, dtype=dtype)
+    rs = np.random.RandomState(n + S)
+    spec = dict(T=T, dt=0.1, goals=np.zeros((G, d)), sigma_start_sample=0.3, sigma_gp_sample=1.0, sigma_goal_sample=0.3)
+    tab = _tables(spec, cuda)
+    start = torch.tensor(rs.uniform(-0.3, 0.3, (B, d)), **ta)
+    goals = torch.tensor(rs.uniform(-0.5, 0.5, (B, G, d)), **ta)
+    comp = CostComposite(n, T, [CostGP(n, T, start, 0.1, dict(sigma_start=0.5, sigma_gp=2.0), ta),
+                                CostGoalPrior(n, T, multi_goal_states=goals, num_particles_per_goal=K, num_samples=S,
+                                              sigma_goal_prior=1.0, tensor_args=ta)], tensor_args=ta)
+    desc = comp.lower(B, G, cuda, dtype).desc(20.0, None)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype)
+    mu0 = torch.tensor(rs.uniform(-0.5, 0.5, (B, G * K, T, d)), **ta)
+    # fp32 softmax amplifies cost rounding (|c|/tau ~ 1e2..1e3 here), so the update is checked on the kernel's OWN costs:
+    # K4 fed the fused kernel's costs and K2's samples of the same draw must reproduce its weights and means.
+    mu = mu0.clone()
+    for it in range(2):
+        xs = _ops().sample(sh, tab, mu, seed=23, draw=it)
+        c = _ops().cost(sh, desc, tab, xs, mu)
+        mu_f = mu.clone()
+        out = _ops().iterate(sh, desc, tab, 0.5, 1, mu_f, seed=23, draw0=it, want_samples=True)
+        assert torch.equal(out['means_pre'], mu)
+        assert float((out['samples'] - xs).abs().max() / xs.abs().max()) < 2e-6
+        assert float((out['costs'] - c).abs().max() / c.abs().max()) < 1e-4
+        mu_k = mu.clone()
+        grad, w = _ops().update(sh, 20.0, 0.5, out['costs'], xs, mu_k)
+        assert float((out['weights'] - w).abs().max()) < 1e-5
+        assert float((out['grad'] - grad).abs().max() / grad.abs().max()) < 1e-4
+        assert float((mu_f - mu_k).abs().max() / mu_k.abs().max()) < 1e-5
+        assert float((out['weights'].sum(-1) - 1).abs().max()) < 1e-5
+        mu = mu_f
+    # two iterations inside ONE cluster launch == two single-iteration launches
+    mu_2 = mu0.clone()
+    _ops().iterate(sh, desc, tab, 0.5, 2, mu_2, seed=23, draw0=0)
+    assert torch.equal(mu_2, mu)
