@@ -577,3 +577,38 @@ def test_cluster_mode_equals_separate_kernels(n, S, cuda):
     mu_2 = mu0.clone()
     _ops().iterate(sh, desc, tab, 0.5, 2, mu_2, seed=23, draw0=0)
     assert torch.equal(mu_2, mu)
+
+
+@pytest.mark.parametrize("T,n,S", [(128, 4, 4096), (256, 14, 2048), (1024, 2, 2048), (1024, 14, 512)])
+def test_c5_sampling_sweep_fp64(T, n, S, cuda):
+    """BASELINE configs[4]: prior construction + sampling for long horizons / many DoF in fp64 (the reference would
+    need a dense M x M factor per particle: M = 28,672 -> 6.6 GB at T=1024, n=14).  Checks: (i) the kernel's
+    samples equal the oracle recurrence on the kernel's own eps; (ii) per-DoF sample moments against the dense
+    2T x 2T covariance (valid because the precision decouples per DoF) where that inverse is cheap."""
+    spec = dict(T=T, dt=0.02, goals=np.zeros((1, 2 * n)), sigma_start_sample=1e-3, sigma_gp_sample=3.0, sigma_goal_sample=1e-3, n_dof=n)
+    tab = _tables(spec, cuda)
+    D, O = P.precision_blocks(T, 0.02, 1e-3, 3.0, 1e-3)
+    fac = P.banded_factor(D, O)
+    sh = _ops().make_shape(1, 1, 1, S, T, n, torch.float64)
+    mu = torch.zeros(1, 1, T, 2 * n, dtype=torch.float64, device=cuda)
+    x, eps = _ops().sample(sh, tab, mu, seed=5, draw=0, want_eps=True)
+    x = from_sminor(x.cpu().numpy())[0, 0]              # [S, T, d]
+    e = from_sminor(eps.cpu().numpy())[0, 0]
+    sub = slice(0, 64)
+    y = SMP.banded_transform(fac['G'], fac['H'], e[sub])
+    assert rel(x[sub], y) < 1e-12
+    if T <= 256:
+        Sigma = np.linalg.inv(P.dense_from_blocks(D, O, 1))
+        sd = np.sqrt(np.diag(Sigma))
+        # pool the n DoFs: S*n independent draws of the same 2T-dimensional Gaussian
+        z = np.concatenate([np.concatenate([x[:, :, i:i + 1], x[:, :, n + i:n + i + 1]], axis=2).reshape(S, 2 * T) for i in range(n)])
+        C = np.cov(z.T)
+        corr_err = np.abs(C - Sigma) / np.outer(sd, sd)
+        assert corr_err.max() < 6.0 / np.sqrt(z.shape[0])
+        assert np.abs(z.mean(0) / sd).max() < 5.0 / np.sqrt(z.shape[0])
+    else:
+        # long horizon: marginal variances against the diagonal of Sigma obtained from the factor itself (L L^T)
+        var = x.reshape(S, T, 2, n).var(axis=(0, 3))
+        Ld = P.dense_scale_tril(fac['G'], fac['H'], 1) if T <= 1024 else None
+        diag = (Ld ** 2).sum(1).reshape(T, 2)
+        assert np.abs(var / diag - 1).max() < 8.0 / np.sqrt(S * n)
