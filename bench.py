@@ -40,7 +40,7 @@ UNIT = "traj-samples/s"
 def workload(name, B):
     """Shapes, sigmas and synthetic inputs (C4 Panda batched / C2 planar batched)."""
     import numpy as np
-    from oracle import scenarios as sc     # synthetic problem generators only (no oracle arithmetic)
+    from stoch_gpmp_b200 import scenarios as sc
     if name == "panda":
         start, goals, spheres = sc.panda_batch(B, G=4, O=5, seed0=0)
         return dict(name="panda_7dof_batched", n_dof=7, T=64, dt=0.05, G=4, K=1, S=512, temperature=1.0, step_size=0.1,

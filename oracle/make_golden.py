@@ -196,7 +196,7 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
           f'[{rec["it0_costs"].min():.3e}, {rec["it0_costs"].max():.3e}]')
 
 
-from oracle.scenarios import (PANDA_SIGMAS, PANDA_START, PLANAR_GOALS, PLANAR_SIGMAS, panda_goals,  # noqa: E402
+from stoch_gpmp_b200.scenarios import (PANDA_SIGMAS, PANDA_START, PLANAR_GOALS, PLANAR_SIGMAS, panda_goals,  # noqa: E402
                               panda_spheres)
 
 PLANAR_MAP = dict(map_dim=[20, 20], cell_size=0.1, num_obst=15, rand_limits=[[-7.5, 7.5], [-7.5, 7.5]], seed=0)

@@ -175,6 +175,8 @@ class LoweredCost:
                 raise NotImplementedError("collision field %s cannot be lowered to the CUDA path"
                                           % type(fields[0]).__name__)
         self._spheres = None
+        self._spheres_src = None
+        self._desc_cache = None
 
     def _need_fk(self, composite, n):
         if not isinstance(composite.FK, SerialChainFK):
@@ -199,39 +201,50 @@ class LoweredCost:
             d.chain_joint[f] = fk.joint[f]
 
     def desc(self, temperature, obstacle_spheres=None):
-        """Fill an sgpmp_cost_desc_t (keeps the tensors it points to alive on self)."""
-        d = _lib.CostDesc()
-        d.dt, d.sigma_start, d.sigma_gp = self.dt, self.sigma_start, self.sigma_gp
-        d.sigma_goal_prior = self.sigma_goal_prior
+        """The sgpmp_cost_desc_t of this cost (keeps the tensors it points to alive on self).  The constant part
+        (sigmas, pointers, map metadata, FK chain) is filled once and cached; a call only patches the temperature and
+        the obstacle-sphere observation, so the per-optimize() host cost stays at a few microseconds."""
+        d = self._desc_cache
+        if d is None:
+            d = _lib.CostDesc()
+            d.dt, d.sigma_start, d.sigma_gp = self.dt, self.sigma_start, self.sigma_gp
+            d.sigma_goal_prior = self.sigma_goal_prior
+            d.start = self.start.data_ptr()
+            d.goals = self.goals.data_ptr() if self.goals is not None else None
+            if self.map is not None:
+                m = self.map_meta
+                d.occ_map = self.map.data_ptr()
+                d.occ_map_u8 = self.map_u8.data_ptr() if self.map_u8 is not None else None
+                d.map_of_problem = self.map_index.data_ptr() if self.map_index is not None else None
+                d.n_maps, d.map_h, d.map_w = self.map.shape[0], m['h'], m['w']
+                d.origin_xi, d.origin_yi = m['oxi'], m['oyi']
+                d.map_inv_cell, d.map_sigma_coll = m['inv_cell'], m['sigma']
+            if self.fk is not None:
+                self._fill_chain(d)
+            if self.self_margin is not None:
+                d.self_margin, d.self_sigma_coll = self.self_margin, self.self_sigma
+            self._desc_cache = d
         d.temperature = float(temperature)
-        d.start = self.start.data_ptr()
-        d.goals = self.goals.data_ptr() if self.goals is not None else None
-        if self.map is not None:
-            m = self.map_meta
-            d.occ_map = self.map.data_ptr()
-            d.occ_map_u8 = self.map_u8.data_ptr() if self.map_u8 is not None else None
-            d.map_of_problem = self.map_index.data_ptr() if self.map_index is not None else None
-            d.n_maps, d.map_h, d.map_w = self.map.shape[0], m['h'], m['w']
-            d.origin_xi, d.origin_yi = m['oxi'], m['oyi']
-            d.map_inv_cell, d.map_sigma_coll = m['inv_cell'], m['sigma']
-        if self.self_margin is not None:
-            d.self_margin, d.self_sigma_coll = self.self_margin, self.self_sigma
-            self._fill_chain(d)
-        if self.sphere_sigma is not None and obstacle_spheres is not None:
-            # (without spheres the reference's LinkDistanceField.compute_cost returns 0, fields.py:64-65)
-            sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
-            if sp.dim() == 2:
-                sp = sp.unsqueeze(0)
-            if sp.shape[0] not in (1, self.B) or sp.shape[-1] != 4:
-                raise ValueError("obstacle_spheres must be [1,O,4] or [B,O,4], got %s" % (tuple(sp.shape),))
-            if sp.shape[1] > _lib.MAX_SPHERES:
-                raise NotImplementedError("more than %d obstacle spheres" % _lib.MAX_SPHERES)
-            self._spheres = sp.contiguous()
-            d.spheres = self._spheres.data_ptr()
-            d.n_spheres = sp.shape[1]
-            d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
-            d.sphere_sigma_coll = self.sphere_sigma
-            self._fill_chain(d)
+        if self.sphere_sigma is not None:
+            if obstacle_spheres is None:
+                # the reference's LinkDistanceField.compute_cost returns 0 without spheres (fields.py:64-65)
+                d.spheres, d.n_spheres = None, 0
+            elif obstacle_spheres is not self._spheres_src:
+                sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
+                if sp.dim() == 2:
+                    sp = sp.unsqueeze(0)
+                if sp.shape[0] not in (1, self.B) or sp.shape[-1] != 4:
+                    raise ValueError("obstacle_spheres must be [1,O,4] or [B,O,4], got %s" % (tuple(sp.shape),))
+                if sp.shape[1] > _lib.MAX_SPHERES:
+                    raise NotImplementedError("more than %d obstacle spheres" % _lib.MAX_SPHERES)
+                self._spheres = sp.contiguous()
+                # the same tensor object passed again (the usual optimize(**obs) loop) is not re-validated, but its
+                # CONTENT is read by the kernel on every call when no copy was needed
+                self._spheres_src = obstacle_spheres if self._spheres.data_ptr() == getattr(obstacle_spheres, 'data_ptr', lambda: 0)() else None
+                d.spheres = self._spheres.data_ptr()
+                d.n_spheres = sp.shape[1]
+                d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
+                d.sphere_sigma_coll = self.sphere_sigma
         return d
 
 

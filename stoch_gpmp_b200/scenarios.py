@@ -1,6 +1,6 @@
 """Synthetic problem generators shared by make_golden.py, the tests and bench.py.
 
-TEST / BENCH INFRASTRUCTURE (see oracle/__init__.py).  Shapes and sigmas follow the reference's two
+Synthetic inputs for benchmarks, examples and tests (no arithmetic of the hot path lives here).  Shapes and sigmas follow the reference's two
 examples (examples/planar_environment.py:14-96, examples/panda_environment.py:29-133) as laid out in
 SURVEY.md §8(d): C1..C4.  Pure numpy; nothing here touches /root/reference.
 """

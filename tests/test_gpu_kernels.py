@@ -442,7 +442,7 @@ def test_fused_full_size_properties(cuda):
     T, n, G, K, S, B = 64, 7, 4, 1, 512, 3
     dtype = torch.float32
     rs = np.random.RandomState(0)
-    from oracle.scenarios import PANDA_START, panda_goals, panda_spheres
+    from stoch_gpmp_b200.scenarios import PANDA_START, panda_goals, panda_spheres
     spec = dict(n_dof=n, T=T, dt=0.05, G=G, K=K, S=S, temperature=1.0, step_size=0.1, start=np.array(PANDA_START),
                 goals=np.array(panda_goals(G, 3)), cost_sigma_start=1e-4, cost_sigma_gp=7e-4, sigma_goal_prior=20., sigma_coll=0.01,
                 spheres=np.array(panda_spheres(5, 3)), sigma_start_sample=1e-3, sigma_gp_sample=0.1, sigma_goal_sample=0.07)

@@ -23,7 +23,7 @@ def _free_port():
 
 
 def _build(dev, dtype, B, lo, hi, S, seed=11):
-    from oracle.scenarios import panda_batch
+    from stoch_gpmp_b200.scenarios import panda_batch
     from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
     from stoch_gpmp_b200.costs.fields import LinkDistanceField
     from stoch_gpmp_b200.planner import StochGPMPBatch

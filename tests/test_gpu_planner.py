@@ -136,7 +136,7 @@ def test_batch_equals_loop_of_singles(cuda):
     from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
     from stoch_gpmp_b200.envs.occupancy import generate_obstacle_map
     from stoch_gpmp_b200.planner import StochGPMP, StochGPMPBatch
-    from oracle.scenarios import PLANAR_COST, PLANAR_SIGMAS, planar_batch
+    from stoch_gpmp_b200.scenarios import PLANAR_COST, PLANAR_SIGMAS, planar_batch
     import random
     B, G, K, S, T, n = 3, 4, 2, 32, 32, 2
     dtype = torch.float32
@@ -227,7 +227,7 @@ def test_c1_planar_as_shipped_shape_fp64(cuda):
     """BASELINE configs[0]: examples/planar_environment.py as shipped — G=3, K=5, S=128, T=64, n=2, fp64, the
     generator's 200x200 map (seed 0), shipped sigmas — three iterations against the oracle."""
     import random
-    from oracle.scenarios import PLANAR_COST, PLANAR_GOALS, PLANAR_SIGMAS
+    from stoch_gpmp_b200.scenarios import PLANAR_COST, PLANAR_GOALS, PLANAR_SIGMAS
     from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
     from stoch_gpmp_b200.envs.map_generator import generate_obstacle_map
     from stoch_gpmp_b200.planner import StochGPMP
@@ -260,7 +260,7 @@ def test_c1_planar_as_shipped_shape_fp64(cuda):
 
 def test_c3_panda_single_problem_shape_fp32(cuda):
     """BASELINE configs[2]: Panda single problem, 4 goals x 512 samples x T=64, fp32, shipped sigmas, O=5 spheres."""
-    from oracle.scenarios import PANDA_COST, PANDA_SIGMAS, PANDA_START, panda_goals, panda_spheres
+    from stoch_gpmp_b200.scenarios import PANDA_COST, PANDA_SIGMAS, PANDA_START, panda_goals, panda_spheres
     from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
     from stoch_gpmp_b200.costs.fields import LinkDistanceField
     from stoch_gpmp_b200.planner import StochGPMP
