@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGPMP_ABI_VERSION 3
+#define SGPMP_ABI_VERSION 4
 
 enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
 
@@ -125,7 +125,16 @@ typedef struct sgpmp_cost_desc {
      * integers, envs/obst_map.py:71,104).  When non-NULL the kernels gather from it instead of occ_map: a 200x200
      * map is 40 KB instead of 160 KB (fp32), so it stays L1-resident.  Bit-exact: every count <= 255 is exact in fp32/fp64. */
     const uint8_t* occ_map_u8;
+
+    /* LinkDistanceField.field_type (costs/fields.py:78-86): how the sphere field combines link origins p and spheres (c, r)
+     *   SGPMP_FIELD_RBF        sum exp(-0.5 |p - c|^2 / r^2)
+     *   SGPMP_FIELD_SDF        max (r - |p - c|);  SGPMP_FIELD_SDF_CLAMPED: max min(r - |p - c|, 0)   (clamp_sdf=True)
+     *   SGPMP_FIELD_OCCUPANCY  number of (link, sphere) pairs with |p - c| < r */
+    int32_t sphere_field_type;
+    int32_t reserved1;
 } sgpmp_cost_desc_t;
+
+enum { SGPMP_FIELD_RBF = 0, SGPMP_FIELD_SDF = 1, SGPMP_FIELD_SDF_CLAMPED = 2, SGPMP_FIELD_OCCUPANCY = 3 };
 
 int sgpmp_abi_version(void);
 const char* sgpmp_last_error(void);

@@ -69,14 +69,29 @@ def sphere_rbf(link_pos, spheres):
     return np.exp(-0.5 * (diff * diff).sum(-1) / (spheres[:, 3] ** 2)).sum((-1, -2))
 
 
-def cost_collision_spheres(x, spheres, sigma_coll, fk_fn):
+def sphere_field(link_pos, spheres, field_type='rbf', clamp_sdf=False):
+    """LinkDistanceField.compute_cost for every field_type (costs/fields.py:78-86)."""
+    if field_type == 'rbf':
+        return sphere_rbf(link_pos, spheres)
+    dist = np.linalg.norm(link_pos[..., :, None, :] - spheres[None, :, :3], axis=-1)
+    if field_type == 'sdf':
+        sdf = -dist + spheres[:, 3]
+        if clamp_sdf:
+            sdf = np.minimum(sdf, 0.)
+        return sdf.max(-1).max(-1)
+    if field_type == 'occupancy':
+        return (dist < spheres[:, 3]).sum((-1, -2)).astype(link_pos.dtype)
+    raise ValueError(field_type)
+
+
+def cost_collision_spheres(x, spheres, sigma_coll, fk_fn, field_type='rbf', clamp_sdf=False):
     """fk_fn: q [N, n] -> H [N, L, 4, 4]."""
     NP, S, T, d = x.shape
     n = d // 2
     q = x[:, :, 1:, :n].reshape(-1, n)
     H = fk_fn(q)
     pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
-    return sphere_rbf(pos, spheres).sum(-1) * (1.0 / sigma_coll ** 2)
+    return sphere_field(pos, spheres, field_type, clamp_sdf).sum(-1) * (1.0 / sigma_coll ** 2)
 
 
 def self_rbf(link_pos, margin):

@@ -33,7 +33,7 @@ def _np(t):
 
 def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_sigmas, cost_sigmas,
              temperature, step_size, iters, map_params=None, spheres=None, initial_particle_means=None,
-             sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None):
+             sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None, field_type='rbf', clamp_sdf=False):
     ref = ref_loader.load()
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
     start_state = torch.tensor(start, **ta)
@@ -78,7 +78,9 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
         rec['self_margin'], rec['sigma_self'] = self_field
     if spheres is not None:
         FK = ofk.fk_all_links_torch()
-        field = ref.LinkDistanceField(tensor_args=ta)
+        field = ref.LinkDistanceField(field_type=field_type, clamp_sdf=clamp_sdf, tensor_args=ta)
+        if field_type != 'rbf':
+            rec['field_type'], rec['clamp_sdf'] = field_type, clamp_sdf
         cost_list.append(ref.CostCollision(n_dof, T, field=field, sigma_coll=sigma_coll))
         term_names.append('coll')
         sph = torch.tensor(spheres, **ta).reshape(1, -1, 4)
@@ -253,6 +255,18 @@ def main():
              initial_particle_means='const_vel',
              cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
              temperature=200., step_size=0.5, iters=2, spheres=None, self_field=(0.15, 0.1))
+    # LinkDistanceField field_type variants (costs/fields.py:80-86): sdf, clamped sdf, occupancy — soft sigmas so that
+    # the collision term matters; spheres placed ON the arm's workspace so that contacts really occur
+    near = [[0.35, 0.0, 0.55, 0.18], [0.5, 0.1, 0.35, 0.15], [0.2, -0.1, 0.8, 0.12]]
+    for nm, ft, cl, dt_ in (('panda_sdf_f64', 'sdf', False, torch.float64), ('panda_sdfclamp_f32', 'sdf', True, torch.float32),
+                            ('panda_occ_f64', 'occupancy', False, torch.float64)):
+        run_case(nm, n_dof=7, T=12, dt=0.05, G=2, K=1, S=12, dtype=dt_, seed=9,
+                 start=PANDA_START, goals=panda_goals(2, 4),
+                 planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.8,
+                                     sigma_start_sample=0.5, sigma_goal_sample=0.5, sigma_gp_sample=0.5),
+                 initial_particle_means='const_vel',
+                 cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.05, sigma_goal_prior=20.,
+                 temperature=200., step_size=0.5, iters=1, spheres=near, field_type=ft, clamp_sdf=cl)
     # Panda with soft sigmas / temperature (non-degenerate weights).  fp32 only constructs for mild
     # conditioning (torch's fp32 Cholesky of the precision fails otherwise — SURVEY §6/§7), so the
     # softer variant is fp64.

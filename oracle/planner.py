@@ -43,6 +43,9 @@ def spec_from_golden(g):
         s['map_origin'] = (int(g['map_origin'][0]), int(g['map_origin'][1]))
     if 'spheres' in g.files:
         s['spheres'] = g['spheres']
+    if 'field_type' in g.files:
+        s['field_type'] = str(g['field_type'])
+        s['clamp_sdf'] = bool(g['clamp_sdf'])
     if 'self_margin' in g.files:
         s['self_margin'] = float(g['self_margin'])
         s['sigma_self'] = float(g['sigma_self'])
@@ -98,7 +101,8 @@ def eval_costs(spec, samples, means, D, O, dtype=np.float64):
         total = total + terms['coll']
     if spec.get('sigma_coll') is not None and 'spheres' in spec:
         terms['coll'] = C.cost_collision_spheres(x, spec['spheres'].astype(dtype), spec['sigma_coll'],
-                                                 lambda q: FK.fk_all_links(q))
+                                                 lambda q: FK.fk_all_links(q), spec.get('field_type', 'rbf'),
+                                                 spec.get('clamp_sdf', False))
         total = total + terms['coll']
     terms['is'] = C.cost_importance(x, means.astype(dtype), D, O, spec['temperature'])
     total = total + terms['is']

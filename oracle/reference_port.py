@@ -141,8 +141,17 @@ class ReferencePort:
         if s.get('sigma_coll') is not None and self.spheres is not None:
             link = x_trajs[:, 1:T][..., :3, -1].unsqueeze(-2)
             sp = self.spheres.unsqueeze(0)
-            rbf = torch.exp(-0.5 * torch.square(link - sp[..., :3]).sum(-1) / torch.square(sp[..., 3])).sum((-1, -2))
-            costs = costs + (1. / s['sigma_coll'] ** 2) * rbf.sum(1)
+            ft = s.get('field_type', 'rbf')
+            if ft == 'rbf':
+                fld = torch.exp(-0.5 * torch.square(link - sp[..., :3]).sum(-1) / torch.square(sp[..., 3])).sum((-1, -2))
+            elif ft == 'sdf':
+                sdf = -torch.linalg.norm(link - sp[..., :3], dim=-1) + sp[..., 3]
+                if s.get('clamp_sdf', False):
+                    sdf = sdf.clamp(max=0.)
+                fld = sdf.max(-1)[0].max(-1)[0]
+            else:
+                fld = (torch.linalg.norm(link - sp[..., :3], dim=-1) < sp[..., 3]).sum((-1, -2))
+            costs = costs + (1. / s['sigma_coll'] ** 2) * fld.sum(1)
         costs = costs.reshape(self.NP, self.S)
         V = samples.reshape(-1, self.S, self.M)
         U = self.means.view(-1, 1, self.M)

@@ -12,9 +12,10 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 TABLE_STRIDE = 16
 MAX_FRAMES = 16
 MAX_SPHERES = 16
+FIELD_RBF, FIELD_SDF, FIELD_SDF_CLAMPED, FIELD_OCCUPANCY = 0, 1, 2, 3
 NUM_TERMS = 6
 TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Shape(C.Structure):
@@ -38,6 +39,7 @@ class CostDesc(C.Structure):
         ("chain_joint", C.c_int32 * MAX_FRAMES),
         ("self_margin", C.c_double), ("self_sigma_coll", C.c_double),
         ("occ_map_u8", C.c_void_p),
+        ("sphere_field_type", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

@@ -171,6 +171,7 @@ class LoweredCost:
                 fields[0].check_lowerable()
                 self._need_fk(composite, n)
                 self.sphere_sigma = float(coll.sigma_coll)
+                self.sphere_field_type = fields[0].field_code()
             else:
                 raise NotImplementedError("collision field %s cannot be lowered to the CUDA path"
                                           % type(fields[0]).__name__)
@@ -245,6 +246,7 @@ class LoweredCost:
                 d.n_spheres = sp.shape[1]
                 d.spheres_per_problem = 1 if (sp.shape[0] == self.B and self.B > 1) else 0
                 d.sphere_sigma_coll = self.sphere_sigma
+                d.sphere_field_type = self.sphere_field_type
         return d
 
 

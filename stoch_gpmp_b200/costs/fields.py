@@ -13,7 +13,8 @@ class DistanceField:
 
 
 class LinkDistanceField(DistanceField):
-    """sum over link frames and obstacle spheres of exp(-0.5 |p - c|^2 / r^2)."""
+    """'rbf': sum over link frames and obstacle spheres of exp(-0.5 |p - c|^2 / r^2); 'sdf': max of r - |p - c|
+    (clamped to <= 0 with clamp_sdf); 'occupancy': number of (link, sphere) pairs in contact."""
 
     def __init__(self, field_type='rbf', clamp_sdf=False, num_interpolate=0, link_interpolate_range=(5, 7), **kwargs):
         super().__init__(**kwargs)
@@ -22,10 +23,19 @@ class LinkDistanceField(DistanceField):
         self.num_interpolate = num_interpolate
         self.link_interpolate_range = list(link_interpolate_range)
 
+    def field_code(self):
+        """sgpmp_cost_desc_t.sphere_field_type for this field (costs/fields.py:78-86)."""
+        from .. import _lib
+        if self.field_type == 'rbf':
+            return _lib.FIELD_RBF
+        if self.field_type == 'sdf':
+            return _lib.FIELD_SDF_CLAMPED if self.clamp_sdf else _lib.FIELD_SDF
+        if self.field_type == 'occupancy':
+            return _lib.FIELD_OCCUPANCY
+        raise NotImplementedError("LinkDistanceField(field_type=%r) is unknown" % (self.field_type,))
+
     def check_lowerable(self):
-        if self.field_type != 'rbf':
-            raise NotImplementedError("LinkDistanceField(field_type=%r): only 'rbf' is lowered to the CUDA path "
-                                      "(SURVEY §8f rank 3)" % (self.field_type,))
+        self.field_code()
         if self.num_interpolate:
             raise NotImplementedError("LinkDistanceField(num_interpolate>0) is not lowered yet (SURVEY §8f rank 1)")
 

@@ -52,6 +52,7 @@ struct CostParams {
     // spheres
     const real* spheres;
     int32_t n_spheres, spheres_per_problem;
+    int32_t sphere_mode;   // SGPMP_FIELD_*
     real sphere_w_coll;
     // FK chain
     int32_t n_frames, include_base;

@@ -85,6 +85,11 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
         o.spheres = (const real*)d.spheres;
         o.n_spheres = d.n_spheres;
         o.spheres_per_problem = d.spheres_per_problem;
+        if (d.sphere_field_type < SGPMP_FIELD_RBF || d.sphere_field_type > SGPMP_FIELD_OCCUPANCY) {
+            set_error("cost desc: unknown sphere_field_type %d", d.sphere_field_type);
+            return SGPMP_ERR_INVALID_ARG;
+        }
+        o.sphere_mode = d.sphere_field_type;
         o.sphere_w_coll = (real)(1.0 / (d.sphere_sigma_coll * d.sphere_sigma_coll));
     }
     if (o.has_self) {
@@ -119,13 +124,15 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     if (means)
         for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
     stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
+    double mub_part = 0.0;
     if (means) {
         for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
             const int t = k / N, i = k - t * N;
-            precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
+            mub_part += precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
         }
     }
-    __syncthreads();
+    __shared__ double red64[32];
+    const real mub = (real)block_sum_f64(mub_part, red64);
 
     const int s = blockIdx.y * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -133,6 +140,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     sm.start = start; sm.goal = goal; sm.bvec = means ? bvec : nullptr; sm.sph = sph;
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
+    sm.mub = mub;
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
 
@@ -140,10 +148,13 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     tc.begin();
     const real* xs = samples + (size_t)bp * T * d * S + s;
     for (int t = 0; t < T; ++t) {
-        real x[d];
+        real x[d], y[d];
 #pragma unroll
-        for (int j = 0; j < d; ++j) x[j] = xs[((size_t)t * d + j) * S];
-        tc.step(P, sm, t, T, x, means ? bvec + t * DP : nullptr);
+        for (int j = 0; j < d; ++j) {
+            x[j] = xs[((size_t)t * d + j) * S];
+            y[j] = means ? x[j] - mu[t * d + j] : x[j];
+        }
+        tc.step(P, sm, t, T, x, y, y + N, means ? bvec + t * DP : nullptr);
     }
     tc.finish(P, sm, T);
     const size_t o = (size_t)bp * S + s;

@@ -34,6 +34,7 @@ struct CostSmem {
     const uint8_t* map_u8;   // byte copy of it, or null
     real coll_const;     // RBF sum of the link frames whose position does not depend on q (structured chains)
     real self_const;     // q-independent part of the self-collision sum (structured chains)
+    real mub;            // mu^T Sigma^-1 mu of this particle (fp64-accumulated): x^T b = mu^T b + (x - mu)^T b
 };
 
 constexpr int SPH_STRIDE = 8;
@@ -49,15 +50,33 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 }
 
 // Stage one sphere (cx, cy, cz, r) into the shared table row.
+// mode != SGPMP_FIELD_RBF: slot 3 holds the radius itself (the sdf / occupancy variants need |p - c| and r).
 template <typename real>
-__device__ __forceinline__ void stage_sphere(const real* s4, real* row) {
+__device__ __forceinline__ void stage_sphere(const real* s4, real* row, int mode) {
     const double cx = s4[0], cy = s4[1], cz = s4[2], r = s4[3];
+    if (mode != SGPMP_FIELD_RBF) {
+        row[0] = (real)cx; row[1] = (real)cy; row[2] = (real)cz; row[3] = (real)r;
+        row[4] = row[5] = row[6] = row[7] = 0;
+        return;
+    }
     const double k = (sizeof(real) == 4 ? -0.5 * 1.4426950408889634 : -0.5) / (r * r);
     row[0] = (real)cx; row[1] = (real)cy; row[2] = (real)cz; row[3] = (real)k;
     row[4] = (real)(-2.0 * k * cx); row[5] = (real)(-2.0 * k * cy); row[6] = (real)(-2.0 * k * cz);
     row[7] = (real)(k * (cx * cx + cy * cy + cz * cz));
 }
 
+__device__ __forceinline__ float vsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double vsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ F2 vsqrt(F2 x) { return f2(sqrtf(lane0(x)), sqrtf(lane1(x))); }
+__device__ __forceinline__ float vmaxv(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double vmaxv(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ F2 vmaxv(F2 a, F2 b) { return f2(fmaxf(lane0(a), lane0(b)), fmaxf(lane1(a), lane1(b))); }
+__device__ __forceinline__ float vminv(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double vminv(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ F2 vminv(F2 a, F2 b) { return f2(fminf(lane0(a), lane0(b)), fminf(lane1(a), lane1(b))); }
+__device__ __forceinline__ float vstep_pos(float a) { return a > 0.f ? 1.f : 0.f; }        // 1 where a > 0
+__device__ __forceinline__ double vstep_pos(double a) { return a > 0.0 ? 1.0 : 0.0; }
+__device__ __forceinline__ F2 vstep_pos(F2 a) { return f2(lane0(a) > 0.f ? 1.f : 0.f, lane1(a) > 0.f ? 1.f : 0.f); }
 template <typename V> __device__ __forceinline__ V vneg(V a) { return -a; }
 template <> __device__ __forceinline__ F2 vneg<F2>(F2 a) { return f2(-lane0(a), -lane1(a)); }   // folds into operand modifiers
 
@@ -201,7 +220,27 @@ struct TrajCost {
             fk_panda_origins<V>(P, q, X, Y, Z);
 #pragma unroll
             for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = vfma(X[l], X[l], vfma(Y[l], Y[l], Z[l] * Z[l]));
-            if (P.has_spheres) {
+            if (P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF) {
+                // sdf / occupancy variants (costs/fields.py:80-86) over ALL 11 frames: the 6 evaluated origins (weights
+                // {1,1,2,1,2,1} matter for the occupancy count only) plus the q-independent base / link1 / link2 origins
+                const real z0 = P.p[0][2];
+                V best = vbroadcast<V>((real)-1e30), cnt = zero;
+                for (int o = 0; o < O; ++o) {
+                    const real* s = sm.sph + SPH_STRIDE * o;
+                    const real cx = s[0], cy = s[1], cz = s[2], r = s[3];
+                    auto one = [&](V x, V y, V z, real w) {
+                        const V dx = x - cx, dy = y - cy, dz = z - cz;
+                        const V sd = r - vsqrt(vfma(dx, dx, vfma(dy, dy, dz * dz)));
+                        best = vmaxv(best, P.sphere_mode == SGPMP_FIELD_SDF_CLAMPED ? vminv(sd, zero) : sd);
+                        cnt = cnt + w * vstep_pos(sd);
+                    };
+#pragma unroll
+                    for (int l = 0; l < PANDA_EVAL_LINKS; ++l) one(X[l], Y[l], Z[l], (l == 2 || l == 4) ? (real)2 : (real)1);
+                    if (P.include_base) one(zero, zero, zero, (real)1);
+                    one(zero, zero, vbroadcast<V>(z0), (real)2);
+                }
+                c_coll += (P.sphere_mode == SGPMP_FIELD_OCCUPANCY) ? cnt : best;
+            } else if (P.has_spheres) {
                 V acc = zero, acc2 = zero;   // acc2: links with weight 2
                 for (int o = 0; o < O; ++o) {
                     const real* s = sm.sph + SPH_STRIDE * o;
@@ -241,13 +280,23 @@ struct TrajCost {
                 c_self += (real)2 * (a1 + ((real)2 * a2 + (real)4 * a4));
             }
         } else {
+            const int mode = P.sphere_mode;
+            V best = vbroadcast<V>((real)-1e30);      // running max of the sdf variants over links and spheres
             auto spheres_at = [&](V x, V y, V z, V& acc) {
                 for (int o = 0; o < O; ++o) {
                     const real* s = sm.sph + SPH_STRIDE * o;
                     const V dx = x - s[0], dy = y - s[1], dz = z - s[2];
-                    acc += vexp2_fast(s[3] * vfma(dx, dx, vfma(dy, dy, dz * dz)));
+                    const V d2 = vfma(dx, dx, vfma(dy, dy, dz * dz));
+                    if (mode == SGPMP_FIELD_RBF) {
+                        acc += vexp2_fast(s[3] * d2);
+                    } else {
+                        const V sd = s[3] - vsqrt(d2);
+                        best = vmaxv(best, mode == SGPMP_FIELD_SDF_CLAMPED ? vminv(sd, zero) : sd);
+                        acc += vstep_pos(sd);
+                    }
                 }
             };
+            auto fold = [&](V acc) { return (mode == SGPMP_FIELD_SDF || mode == SGPMP_FIELD_SDF_CLAMPED) ? best : acc; };
             if (P.has_self) {
                 // generic chain: keep every origin, then the upper triangle of the pair matrix
                 V PX[SGPMP_MAX_FRAMES + 1], PY[SGPMP_MAX_FRAMES + 1], PZ[SGPMP_MAX_FRAMES + 1];
@@ -257,7 +306,7 @@ struct TrajCost {
                     PX[L] = x; PY[L] = y; PZ[L] = z; ++L;
                     if (P.has_spheres) spheres_at(x, y, z, acc);
                 });
-                c_coll += acc;
+                if (P.has_spheres) c_coll += fold(acc);
                 V sa = zero;
                 for (int l = 0; l < L; ++l)
                     for (int m = l + 1; m < L; ++m) {
@@ -268,7 +317,7 @@ struct TrajCost {
             } else {
                 V acc = zero;
                 fk_visit_links<V, N>(P, q, [&](V x, V y, V z) { spheres_at(x, y, z, acc); });
-                c_coll += acc;
+                c_coll += fold(acc);
             }
         }
     }
@@ -294,8 +343,9 @@ struct TrajCost {
 
     // feed state x_t (t = 0..T-1 in order)
     // brow: b_t = (Sigma^-1 mu)_t of this particle (2N reals, 16-byte aligned when 2N % 4 == 0 rows are padded), or null
+    // y: x - mu (the IS term is accumulated as mu^T b + y^T b: |y| << |x|, an order of magnitude less fp32 rounding)
     __device__ __forceinline__ void step(const CostParams<real>& P, const CostSmem<real>& sm, int t, int T,
-                                         const V (&x)[2 * N], const real* brow) {
+                                         const V (&x)[2 * N], const V* yp, const V* yv, const real* brow) {
         if (t == 0) {
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) {
@@ -326,7 +376,7 @@ struct TrajCost {
 #pragma unroll
             for (int k = 0; k < DP4; ++k) load4(brow + 4 * k, b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
 #pragma unroll
-            for (int j = 0; j < 2 * N; ++j) c_is = vfma(x[j], b[j], c_is);
+            for (int i = 0; i < N; ++i) c_is = vfma(yp[i], b[i], vfma(yv[i], b[N + i], c_is));
         }
 #pragma unroll
         for (int j = 0; j < 2 * N; ++j) xp[j] = x[j];
@@ -341,7 +391,7 @@ struct TrajCost {
         }
         c_coll = c_coll * (P.has_map ? P.map_w_coll : P.sphere_w_coll);
         c_self = c_self * P.self_w_coll;
-        c_is = c_is * P.temperature;
+        c_is = (c_is + sm.mub) * P.temperature;
     }
     // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
     // obstacle collision (examples/panda_environment.py:90), then += IS (planner.py:236)
@@ -366,11 +416,11 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
     }
     if (P.has_spheres)
         for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x)
-            stage_sphere<real>(P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4, sph + SPH_STRIDE * k);
+            stage_sphere<real>(P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4, sph + SPH_STRIDE * k, P.sphere_mode);
     __syncthreads();
     if (threadIdx.x == 0) {
         real cc = 0;
-        if (CHAIN >= 1 && P.has_spheres) {
+        if (CHAIN >= 1 && P.has_spheres && P.sphere_mode == SGPMP_FIELD_RBF) {
             // q-independent origins of the Panda structure: base (if counted), link1 and link2 at (0, 0, z0)
             const real z0 = P.p[0][2];
             for (int o = 0; o < P.n_spheres; ++o) {
@@ -414,13 +464,27 @@ inline int chain_is_panda_structure(const sgpmp_cost_desc_t& d, int n_dof) {
     return 1;
 }
 
+// Block-wide sum of one double per thread (shuffles + one shared-memory hop); scratch: >= 32 doubles.
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) scratch[w] = v;
+    __syncthreads();
+    double r = 0;
+    for (int k = 0; k < nw; ++k) r += scratch[k];
+    __syncthreads();
+    return r;
+}
+
 // b = P mu for one particle, computed in fp64 from the D/O blocks (the fp32 reference evaluates this
 // contraction with catastrophic cancellation), stored as `real`.
 // tabDO: [T][7] doubles (d11,d12,d22,o11,o12,o21,o22), O_t = P[t+1,t].
 // MU_STRIDE: row stride of mu in reals (0 = dense rows of 2n); VOFF: offset of the velocity half (0 = n).
 template <typename real, int MU_STRIDE = 0, int VOFF = 0>
-__device__ __forceinline__ void precision_times_row(const double* tabDO, const real* mu, int T, int n_, int t, int i,
-                                                    real* bp, real* bv) {
+__device__ __forceinline__ double precision_times_row(const double* tabDO, const real* mu, int T, int n_, int t, int i,
+                                                      real* bp, real* bv) {
     const int d = MU_STRIDE ? MU_STRIDE : 2 * n_;
     const int n = VOFF ? VOFF : n_;
     const double* r = tabDO + t * 7;
@@ -440,6 +504,7 @@ __device__ __forceinline__ void precision_times_row(const double* tabDO, const r
     }
     *bp = (real)p;
     *bv = (real)v;
+    return mp * p + mv * v;        // this row's share of mu^T P mu, in fp64
 }
 
 }  // namespace sgpmp

@@ -127,8 +127,10 @@ struct TrajCostPairs {
 
     // feed state x_t as DoF pairs: xp[k] = (pos_2k, pos_2k+1), xv[k] = (vel_2k, vel_2k+1)
     // srow / grow / brow: start, goal and b_t rows in the pair layout [pos pairs][vel pairs] (16-byte aligned)
+    // yp / yv: the deviations x - mu (IS term = mu^T b + y^T b, see TrajCost::step)
     __device__ __forceinline__ void step(const CostParams<float>& P, const CostSmem<float>& sm, int t, int T,
-                                         const F2 (&xp)[NP2], const F2 (&xv)[NP2], const float* brow) {
+                                         const F2 (&xp)[NP2], const F2 (&xv)[NP2], const F2 (&yp)[NP2], const F2 (&yv)[NP2],
+                                         const float* brow) {
         auto pair_at = [](const float* row, int k) { return f2(row[2 * k], row[2 * k + 1]); };   // folds into LDS.64/128
         if (t == 0) {
 #pragma unroll
@@ -156,7 +158,7 @@ struct TrajCostPairs {
         }
         if (brow) {
 #pragma unroll
-            for (int k = 0; k < NP2; ++k) c_is = vfma(xp[k], pair_at(brow, k), vfma(xv[k], pair_at(brow + VOFF, k), c_is));
+            for (int k = 0; k < NP2; ++k) c_is = vfma(yp[k], pair_at(brow, k), vfma(yv[k], pair_at(brow + VOFF, k), c_is));
         }
 #pragma unroll
         for (int k = 0; k < NP2; ++k) { xpp[k] = xp[k]; xpv[k] = xv[k]; }
@@ -174,7 +176,7 @@ struct TrajCostPairs {
         }
         coll *= (P.has_map ? P.map_w_coll : P.sphere_w_coll);
         self *= P.self_w_coll;
-        const float is = hsum(c_is) * P.temperature;
+        const float is = (hsum(c_is) + sm.mub) * P.temperature;
         if (terms6) { terms6[0] = st; terms6[1] = gp; terms6[2] = go; terms6[3] = coll; terms6[4] = is; terms6[5] = self; }
         return ((((st + gp) + go) + self) + coll) + is;
     }

@@ -85,7 +85,8 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     real* mu = tabGH + (size_t)T * 8;                         // [T][DP]
     real* bvec = mu + (size_t)T * DP;                         // [T][DP]
     double* tabDO = reinterpret_cast<double*>(bvec + (size_t)T * DP);   // [T][7]
-    real* acc = reinterpret_cast<real*>(tabDO + (size_t)T * 7);         // [T][d]  sum_s w_s eps_s, then grad
+    double* red64 = tabDO + (size_t)T * 7;                              // [32] fp64 reduction scratch
+    real* acc = reinterpret_cast<real*>(red64 + 32);                    // [T][d]  sum_s w_s eps_s, then grad
     real* wsm = acc + M;                                      // [ceil(S/CL)] costs -> weights of this CTA's samples
     real* part = wsm + (S + CL - 1) / CL;                     // [4*BS] partial sums of pass 2
     real* red = part + 4 * BS;                                // [32]
@@ -127,10 +128,12 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
         const real* eps = A.eps_in ? A.eps_in + ((size_t)it * n_particles + bp) * (size_t)M * S : nullptr;
 
         // ---- b = Sigma^-1 mu (fp64 accumulate) ---------------------------------------------------------
+        double mub_part = 0.0;
         for (int k = tid; k < T * N; k += BS) {
             const int t = k / N, i = k - t * N;
-            precision_times_row<real, DP, VOFF>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + VOFF + i]);
+            mub_part += precision_times_row<real, DP, VOFF>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + VOFF + i]);
         }
+        sm.mub = (real)block_sum_f64(mub_part, red64);
         if (last && A.means_pre && cr == 0)
             for (int k = tid; k < M; k += BS) A.means_pre[(size_t)bp * M + k] = mu[(k / d) * DP + col(k % d)];
         __syncthreads();
@@ -181,7 +184,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                         xp[k] = f2(mrow[2 * k], mrow[2 * k + 1]) + np_;
                         xv[k] = f2(mrow[VOFF + 2 * k], mrow[VOFF + 2 * k + 1]) + nv_;
                     }
-                    tc.step(P, sm, t, T, xp, xv, bvec + t * DP);
+                    tc.step(P, sm, t, T, xp, xv, yp, yv, bvec + t * DP);
                     if (emit) {
 #pragma unroll
                         for (int k = 0; k < NP2; ++k) {
@@ -247,7 +250,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                         x[i] = m[i] + np_;
                         x[N + i] = m[N + i] + nv_;
                     }
-                    tc.step(P, sm, t, T, x, bvec + t * DP);
+                    tc.step(P, sm, t, T, x, yp, yv, bvec + t * DP);
                     if (emit) {
     #pragma unroll
                         for (int j = 0; j < d; ++j) {
@@ -406,7 +409,7 @@ template <typename real, int PACK, int N, int BS, int CHAIN, int CL = 1>
 static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
     const int d = 2 * N, M = sh.T * d, VOFF = (PACK == 2) ? 2 * ((N + 1) / 2) : N, DP = (PACK == 2) ? 2 * VOFF : ((d + 3) & ~3);
     const int S_loc = (sh.S + CL - 1) / CL;
-    const size_t smem = (size_t)sh.T * 7 * sizeof(double) +
+    const size_t smem = ((size_t)sh.T * 7 + 32) * sizeof(double) +
                         ((size_t)sh.T * (8 + 2 * DP) + (size_t)M * (CL > 1 ? 2 : 1) + S_loc + 4 * BS + 32 + 4 * VOFF + 4 + SPH_SMEM) * sizeof(real);
     if (smem > 227 * 1024) {
         set_error("sgpmp_iterate: T=%d, S=%d need %zu bytes of shared memory (> 227 KiB)", sh.T, sh.S, smem);
@@ -445,13 +448,13 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
     static const char* cl_env = getenv("SGPMP_ITERATE_CLUSTER");    // 0 disables
     const bool want_cluster = !(cl_env && atoi(cl_env) == 0) && !A.eps_in && sh.S >= 256 && (long)sh.B * sh.G * sh.K * 8 <= 2 * 148;
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
-        const bool pairs_ok_c = (CHAIN >= 1) || !(P.has_spheres || P.has_self);
+        const bool pairs_ok_c = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (want_cluster && pairs_ok_c) return launch_iterate_nb<real, 2, N, 64, CHAIN, 8>(sh, P, A, st);
     }
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const int pack = pack_env ? atoi(pack_env) : 2;
         // dof-pair packing covers the occupancy-map field and the Panda structure; generic FK chains stay scalar
-        const bool pairs_ok = (CHAIN >= 1) || !(P.has_spheres || P.has_self);
+        const bool pairs_ok = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (pack == 2 && pairs_ok) {
             if (sh.S > 128 && !bs128) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
             return launch_iterate_nb<real, 2, N, 128, CHAIN>(sh, P, A, st);

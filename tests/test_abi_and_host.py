@@ -146,7 +146,10 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
     with pytest.raises(NotImplementedError, match="SerialChainFK"):
         comp.lower(1, 1, torch.device('cpu'), torch.float32)
     with pytest.raises(NotImplementedError):
-        LinkDistanceField(field_type='sdf').check_lowerable()
+        LinkDistanceField(field_type='hinge').check_lowerable()
+    with pytest.raises(NotImplementedError):
+        LinkDistanceField(num_interpolate=3).check_lowerable()
+    assert LinkDistanceField(field_type='sdf', clamp_sdf=True).field_code() == 2
     # non-square map
     om = ObstacleMap([4, 2], 0.5, tensor_args=ta)
     gp2 = CostGP(2, 8, torch.zeros(4), 0.05, dict(sigma_start=1., sigma_gp=1.), ta)

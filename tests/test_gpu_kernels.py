@@ -63,7 +63,8 @@ def _lowered(spec, dev, dtype, B=1):
         cl.append(CostCollision(n, T, field=om, sigma_coll=spec['sigma_coll']))
     if 'spheres' in spec:
         FK = PandaFK()
-        cl.append(CostCollision(n, T, field=LinkDistanceField(tensor_args=ta), sigma_coll=spec['sigma_coll']))
+        cl.append(CostCollision(n, T, field=LinkDistanceField(field_type=spec.get('field_type', 'rbf'), clamp_sdf=spec.get('clamp_sdf', False),
+                                                              tensor_args=ta), sigma_coll=spec['sigma_coll']))
     comp = CostComposite(n, T, cl, FK=FK, tensor_args=ta)
     G = spec['G']
     return comp, comp.lower(B, G, dev, dtype)
@@ -240,7 +241,9 @@ def test_cost_terms_match_reference(name, cuda):
         _, tot_o = OP.eval_costs(spec, g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O)
         is_o = OP.C.cost_importance(g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O, spec['temperature'])
         assert rel(terms[4], is_o) < (TOL_F32 if f32 else 1e-10)
-        assert rel(costs, tot_o) < (TOL_F32 if f32 else 1e-10)
+        # fp32 totals vs the fp64 oracle: the GP term squares DIFFERENCES of fp32 states (|x| ~ 3, ulp 2.4e-7, e ~ 0.05),
+        # so 1e-5 is the rounding floor of the inputs themselves on the soft-sigma cases; 3e-5 bounds it
+        assert rel(costs, tot_o) < (3e-5 if f32 else 1e-10)
         if not f32:
             assert rel(terms[4], g[pre + 'term_is']) < 1e-9
             assert rel(costs, g[pre + 'costs']) < 1e-10
@@ -344,7 +347,7 @@ def test_fused_iteration_matches_reference(name, cuda):
         else:
             # fp32: total costs vs the accurate (fp64) oracle; weights/update from the kernel's own costs
             r = OP.iterate(spec, g[pre + 'means_pre'], eps_ref_to_traj(g[pre + 'eps'], T, d))
-            assert rel(costs, r['costs']) < TOL_F32
+            assert rel(costs, r['costs']) < 3e-5      # fp32 rounding floor of the GP term, see test_cost_terms_match_reference
             from oracle import update as U
             mp, grad, w = U.update(g[pre + 'means_pre'].astype(np.float64), r['samples'], costs.astype(np.float64),
                                    spec['temperature'], spec['step_size'])
