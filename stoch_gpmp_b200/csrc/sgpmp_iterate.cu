@@ -444,12 +444,22 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
     static const char* force_bs = getenv("SGPMP_ITERATE_BS");       // tuning aids
     static const char* pack_env = getenv("SGPMP_ITERATE_PACK");     // 0 scalar, 2 dof pairs (default)
     const bool bs128 = force_bs && atoi(force_bs) == 128;
-    // few problems: split every particle's samples over a cluster of 8 CTAs (DSMEM reductions) to use more SMs
+    // few problems: split every particle's samples over a cluster of 8 / 4 / 2 CTAs (DSMEM reductions) so that the
+    // launch still covers the 148 SMs: the largest cluster that keeps <= 2 CTAs per SM and >= 64 samples per CTA
     static const char* cl_env = getenv("SGPMP_ITERATE_CLUSTER");    // 0 disables
-    const bool want_cluster = !(cl_env && atoi(cl_env) == 0) && !A.eps_in && sh.S >= 256 && (long)sh.B * sh.G * sh.K * 8 <= 2 * 148;
+    const long n_part = (long)sh.B * sh.G * sh.K;
+    int cl = 1;
+    if (!(cl_env && atoi(cl_env) == 0) && !A.eps_in) {
+        for (int c = 8; c >= 2; c >>= 1)
+            if (n_part * c <= 2 * 148 && sh.S >= 64 * c && (c == 8 ? sh.S >= 256 : true)) { cl = c; break; }
+    }
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const bool pairs_ok_c = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
-        if (want_cluster && pairs_ok_c) return launch_iterate_nb<real, 2, N, 64, CHAIN, 8>(sh, P, A, st);
+        if (pairs_ok_c) {
+            if (cl == 8) return launch_iterate_nb<real, 2, N, 64, CHAIN, 8>(sh, P, A, st);
+            if (cl == 4) return launch_iterate_nb<real, 2, N, 128, CHAIN, 4>(sh, P, A, st);
+            if (cl == 2) return launch_iterate_nb<real, 2, N, 128, CHAIN, 2>(sh, P, A, st);
+        }
     }
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const int pack = pack_env ? atoi(pack_env) : 2;

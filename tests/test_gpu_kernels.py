@@ -615,3 +615,35 @@ def test_c5_sampling_sweep_fp64(T, n, S, cuda):
         Ld = P.dense_scale_tril(fac['G'], fac['H'], 1) if T <= 1024 else None
         diag = (Ld ** 2).sum(1).reshape(T, 2)
         assert np.abs(var / diag - 1).max() < 8.0 / np.sqrt(S * n)
+
+
+@pytest.mark.parametrize("B,S", [(2, 512), (6, 256), (12, 192), (20, 128)])
+def test_cluster_sizes_agree_with_one_problem_at_a_time(B, S, cuda):
+    """The cluster size (8 / 4 / 2 / 1) is chosen from the number of particles and samples; a batch of B problems
+    must give, per problem, what that problem gives when launched alone (which uses the largest cluster)."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, CostGoalPrior
+    n, T, G, K = 7, 8, 4, 1
+    d = 2 * n
+    dtype = torch.float32
+    ta = dict(device=cuda, dtype=dtype)
+    rs = np.random.RandomState(B)
+    spec = dict(T=T, dt=0.1, goals=np.zeros((G, d)), sigma_start_sample=0.3, sigma_gp_sample=1.0, sigma_goal_sample=0.3)
+    tab = _tables(spec, cuda)
+    start = torch.tensor(rs.uniform(-0.3, 0.3, (B, d)), **ta)
+    goals = torch.tensor(rs.uniform(-0.5, 0.5, (B, G, d)), **ta)
+    mu0 = torch.tensor(rs.uniform(-0.5, 0.5, (B, G * K, T, d)), **ta)
+
+    def run(lo, hi):
+        comp = CostComposite(n, T, [CostGP(n, T, start[lo:hi], 0.1, dict(sigma_start=0.5, sigma_gp=2.0), ta),
+                                    CostGoalPrior(n, T, multi_goal_states=goals[lo:hi], num_particles_per_goal=K, num_samples=S,
+                                                  sigma_goal_prior=1.0, tensor_args=ta)], tensor_args=ta)
+        desc = comp.lower(hi - lo, G, cuda, dtype).desc(20.0, None)
+        sh = _ops().make_shape(hi - lo, G, K, S, T, n, dtype, problem_gid0=lo)
+        mu = mu0[lo:hi].clone()
+        out = _ops().iterate(sh, desc, tab, 0.5, 2, mu, seed=3, draw0=0)
+        return mu, out['costs']
+    mu_all, c_all = run(0, B)
+    for b in (0, B - 1):
+        mu_b, c_b = run(b, b + 1)
+        assert float((c_all[b] - c_b[0]).abs().max() / c_b.abs().max()) < 1e-5
+        assert float((mu_all[b] - mu_b[0]).abs().max() / mu_b.abs().max()) < 1e-3       # fp32 softmax sensitivity
