@@ -1,17 +1,19 @@
 """The reference's examples/panda_environment.py on stoch_gpmp_b200 (headless, no pybullet / torch_robotics).
 
-Same cost list and parameters as the reference script (examples/panda_environment.py:29-146) minus the EE SE(3)
-goal term (needs torch_robotics' SE3_distance) — the IK goal of pybullet is replaced by a fixed joint-space goal
-and the obstacle spheres are drawn with numpy instead of the simulator.
+Same cost list and parameters as the reference script (examples/panda_environment.py:29-146): CostGP, CostGoalPrior,
+self-collision, obstacle spheres and the EE SE(3) goal (CostGoal + EESE3DistanceField; SE3_distance as restated in
+DESIGN.md §3).  The IK goal of pybullet is replaced by a fixed joint-space goal and the obstacle spheres are drawn
+with numpy instead of the simulator.
 """
+import math
 import time
 
 import numpy as np
 import torch
 
 from stoch_gpmp_b200.planner import StochGPMP
-from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
-from stoch_gpmp_b200.costs.fields import LinkDistanceField, LinkSelfDistanceField
+from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoal, CostGoalPrior
+from stoch_gpmp_b200.costs.fields import EESE3DistanceField, LinkDistanceField, LinkSelfDistanceField
 from stoch_gpmp_b200.robots import PandaFK
 from stoch_gpmp_b200 import ops
 
@@ -27,6 +29,15 @@ if __name__ == '__main__':
     dt = 0.05
     np.random.seed(seed)
 
+    # world setup (examples/panda_environment.py:38-43): target_rot = Rz(-pi) Ry(-pi), target_pos = (.3, .3, .3)
+    c, s = math.cos(-math.pi), math.sin(-math.pi)
+    Rz = torch.tensor([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]], dtype=torch.float64)
+    Ry = torch.tensor([[c, 0., s], [0., 1., 0.], [-s, 0., c]], dtype=torch.float64)
+    target_H = torch.eye(4, dtype=torch.float64)
+    target_H[:3, :3] = Rz @ Ry
+    target_H[:3, 3] = torch.tensor([.3, .3, .3], dtype=torch.float64)
+    target_H = target_H.to(**tensor_args).unsqueeze(0)
+
     panda_fk = PandaFK()
     n_dof = panda_fk._n_dofs
     start_q = torch.tensor([0.012, -0.57, 0., -2.81, 0., 3.037, 0.741], **tensor_args)
@@ -36,15 +47,17 @@ if __name__ == '__main__':
 
     panda_self_link = LinkSelfDistanceField(margin=0.03, tensor_args=tensor_args)
     panda_collision_link = LinkDistanceField(tensor_args=tensor_args)
+    panda_goal = EESE3DistanceField(target_H, tensor_args=tensor_args)
     prior_sigmas = dict(sigma_start=0.0001, sigma_gp=0.0007)
-    sigma_self, sigma_coll, sigma_goal_prior = 0.01, 0.01, 20.
+    sigma_self, sigma_coll, sigma_goal, sigma_goal_prior = 0.01, 0.01, 0.00007, 20.
     cost_prior = CostGP(n_dof, traj_len, start_state, dt, prior_sigmas, tensor_args)
     cost_self = CostCollision(n_dof, traj_len, field=panda_self_link, sigma_coll=sigma_self)
     cost_coll = CostCollision(n_dof, traj_len, field=panda_collision_link, sigma_coll=sigma_coll)
     cost_goal_prior = CostGoalPrior(n_dof, traj_len, multi_goal_states=multi_goal_states,
                                     num_particles_per_goal=num_particles_per_goal, num_samples=num_samples,
                                     sigma_goal_prior=sigma_goal_prior, tensor_args=tensor_args)
-    cost_composite = CostComposite(n_dof, traj_len, [cost_prior, cost_goal_prior, cost_self, cost_coll], FK=panda_fk)
+    cost_goal = CostGoal(n_dof, traj_len, field=panda_goal, sigma_goal=sigma_goal)
+    cost_composite = CostComposite(n_dof, traj_len, [cost_prior, cost_goal_prior, cost_self, cost_coll, cost_goal], FK=panda_fk)
 
     planner = StochGPMP(
         num_particles_per_goal=num_particles_per_goal, num_samples=num_samples, traj_len=traj_len, dt=dt, n_dof=n_dof,
@@ -71,3 +84,5 @@ if __name__ == '__main__':
     sph = obs['obstacle_spheres'][0]
     dist = (pos[:, :, None, :] - sph[None, None, :, :3]).norm(dim=-1) - sph[None, None, :, 3]
     print('final means: min link-origin clearance to the spheres = %.3f m' % dist.min().item())
+    ee = pos.reshape(-1, traj_len, pos.shape[1], 3)[:, -1, -1]                         # ee_link origin at t = T-1
+    print('final means: EE position error to the target = %s m' % (ee - target_H[0, :3, 3]).norm(dim=-1).cpu().numpy().round(4))

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGPMP_ABI_VERSION 4
+#define SGPMP_ABI_VERSION 5
 
 enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
 
@@ -60,9 +60,13 @@ enum {
 
 #define SGPMP_MAX_FRAMES 16
 #define SGPMP_MAX_SPHERES 16
-#define SGPMP_NUM_TERMS 6
-/* total = ((((start + gp) + goal) + self) + coll) + is */
-enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_COLL = 3, SGPMP_TERM_IS = 4, SGPMP_TERM_SELF = 5 };
+#define SGPMP_MAX_INTERP 8        /* link interpolation: extra points per link pair */
+#define SGPMP_MAX_LINK_POINTS 48  /* link frames + interpolated points of one field */
+#define SGPMP_NUM_TERMS 7
+/* total = (((((start + gp) + goal) + self) + coll) + ee) + is  — the order of the shipped cost lists
+ * (examples/panda_environment.py:90), then the IS term (planner.py:236) */
+enum { SGPMP_TERM_START = 0, SGPMP_TERM_GP = 1, SGPMP_TERM_GOAL = 2, SGPMP_TERM_COLL = 3, SGPMP_TERM_IS = 4, SGPMP_TERM_SELF = 5,
+       SGPMP_TERM_EE = 6 };
 
 /* Problem-batch shape.  problem_gid0 is the GLOBAL index of problem 0 of this shard: the Philox
  * counters are keyed by global problem/particle ids so that results do not depend on how the batch is
@@ -81,6 +85,8 @@ typedef struct sgpmp_shape {
  *       ObstacleMap         envs/obst_map.py:108-188     (occupancy grid lookup)
  *       LinkDistanceField   costs/fields.py:30-86 'rbf'  (FK link positions vs obstacle spheres)
  *       LinkSelfDistanceField costs/fields.py:89-127     (FK link positions vs each other; own sigma)
+ *   CostGoal        cost_functions.py:282-321  sigma_goal + EESE3DistanceField (costs/fields.py:130-153): SE(3) distance
+ *                                              of the LAST link frame to a target pose at the LAST time step
  *   IS term         planner.py:233-236         temperature * x^T Sigma^-1 mu
  * FK chain = the callable the reference passes as CostComposite(FK=...) (cost_functions.py:39-52),
  * restated as a serial chain of fixed transforms + revolute z joints. */
@@ -132,6 +138,26 @@ typedef struct sgpmp_cost_desc {
      *   SGPMP_FIELD_OCCUPANCY  number of (link, sphere) pairs with |p - c| < r */
     int32_t sphere_field_type;
     int32_t reserved1;
+
+    /* Link interpolation (LinkDistanceField / LinkSelfDistanceField num_interpolate, link_interpolate_range;
+     * costs/fields.py:68-74, :117-123): for i in [lo, hi) the points X_i + (X_{i+1} - X_i) alpha_k, k < n, are appended to the
+     * link-frame origins (indices count the base frame when include_base).  alpha is host data: the reference evaluates
+     * torch.linspace(0, 1, n + 2)[1:n+1] in float32 and casts it, so the host passes exactly those values.  n = 0: off. */
+    int32_t sphere_interp_n, sphere_interp_lo, sphere_interp_hi;
+    int32_t self_interp_n, self_interp_lo, self_interp_hi;
+    double sphere_interp_alpha[SGPMP_MAX_INTERP];
+    double self_interp_alpha[SGPMP_MAX_INTERP];
+
+    /* End-effector SE(3) goal (CostGoal + EESE3DistanceField; needs the FK chain):
+     *   dist = ee_w_pos |p_ee - p*| + ee_w_rot acos(clamp((tr(R_ee^T R*) - 1)/2, -1, 1)),  cost = dist^2 (ee_square) or dist,
+     *   weight 1/ee_sigma_goal^2, evaluated on the last link frame at t = T-1 only.
+     * SE3_distance itself lives in the absent torch_robotics: this definition is oracle/se3.py's (parity unpinned there). */
+    double ee_sigma_goal;            /* <= 0: absent */
+    double ee_target_R[9];           /* target rotation, row-major */
+    double ee_target_p[3];
+    double ee_w_pos, ee_w_rot;
+    int32_t ee_square;
+    int32_t reserved2;
 } sgpmp_cost_desc_t;
 
 enum { SGPMP_FIELD_RBF = 0, SGPMP_FIELD_SDF = 1, SGPMP_FIELD_SDF_CLAMPED = 2, SGPMP_FIELD_OCCUPANCY = 3 };
@@ -168,7 +194,7 @@ int sgpmp_sample(const sgpmp_shape_t* shape, const double* tables, const void* m
                  void* samples, void* eps_out, void* stream);
 
 /* K3 — per-trajectory-sample cost: CostComposite.eval (cost_functions.py:47-58) + the IS term
- * (planner.py:229-237).  costs [B,NP,S]; terms optional [SGPMP_NUM_TERMS, B, NP, S].
+ * (planner.py:229-237).  costs [B,NP,S]; terms optional [SGPMP_NUM_TERMS, B, NP, S] (SGPMP_TERM_* order).
  * means == NULL drops the IS term (then tables may be NULL): that is CostComposite.eval alone. */
 int sgpmp_cost(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
                const void* samples, const void* means, void* costs, void* terms, void* stream);

@@ -13,6 +13,8 @@ Reference call sites restated (all in /root/reference/stoch_gpmp):
   ObstacleMap.get_collisions  envs/obst_map.py:164-182
   LinkDistanceField.compute_cost ('rbf')  costs/fields.py:63-79
   LinkSelfDistanceField.compute_cost      costs/fields.py:114-124
+  link interpolation          costs/fields.py:68-74, :117-123
+  CostGoal.eval + EESE3DistanceField.compute_cost   costs/cost_functions.py:308-321, costs/fields.py:142-150
   importance-sampling term    planner.py:229-237   tau * x^T Sigma^-1 mu
 
 Every function takes samples x [NP, S, T, d] and returns [NP, S].
@@ -84,13 +86,41 @@ def sphere_field(link_pos, spheres, field_type='rbf', clamp_sdf=False):
     raise ValueError(field_type)
 
 
-def cost_collision_spheres(x, spheres, sigma_coll, fk_fn, field_type='rbf', clamp_sdf=False):
+def interp_alpha(num_interpolate, dtype):
+    """alpha of costs/fields.py:69: torch.linspace(0, 1, n + 2) is evaluated in torch's DEFAULT dtype (float32)
+    and only then cast to the link dtype, so fp64 runs see float32-rounded fractions.  Restated: float32
+    step = 1/(n+1); first half start + i*step, second half end - (steps-1-i)*step with the product fused into the
+    subtraction (ATen RangeFactories, vectorised CPU kernel); checked against torch for n = 1..8 in
+    tests/test_oracle_golden.py."""
+    steps = num_interpolate + 2
+    step = np.float32(1.0) / np.float32(steps - 1)
+    half = steps // 2
+    a = np.array([np.float32(i) * step if i < half else np.float32(1.0 - np.float64(step) * (steps - 1 - i))
+                  for i in range(steps)], dtype=np.float32)
+    return a[1:num_interpolate + 1].astype(dtype)
+
+
+def interpolate_links(link_pos, num_interpolate=0, interp_range=(5, 7)):
+    """link_pos [..., L, 3] -> [..., L + n*(hi-lo), 3]: extra evaluation points X_i + (X_{i+1} - X_i) alpha between
+    link frames i and i+1 for i in [lo, hi), appended after the frames (costs/fields.py:68-74)."""
+    if not num_interpolate:
+        return link_pos
+    alpha = interp_alpha(num_interpolate, link_pos.dtype)[:, None]
+    out = [link_pos]
+    for i in range(interp_range[0], interp_range[1]):
+        X1, X2 = link_pos[..., i:i + 1, :], link_pos[..., i + 1:i + 2, :]
+        out.append(X1 + (X2 - X1) * alpha)
+    return np.concatenate(out, axis=-2)
+
+
+def cost_collision_spheres(x, spheres, sigma_coll, fk_fn, field_type='rbf', clamp_sdf=False, num_interpolate=0,
+                           interp_range=(5, 7)):
     """fk_fn: q [N, n] -> H [N, L, 4, 4]."""
     NP, S, T, d = x.shape
     n = d // 2
     q = x[:, :, 1:, :n].reshape(-1, n)
     H = fk_fn(q)
-    pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
+    pos = interpolate_links(H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3), num_interpolate, interp_range)
     return sphere_field(pos, spheres, field_type, clamp_sdf).sum(-1) * (1.0 / sigma_coll ** 2)
 
 
@@ -101,12 +131,26 @@ def self_rbf(link_pos, margin):
     return np.exp((diff * diff).sum(-1) / (-margin ** 2 * 2)).sum((-1, -2))
 
 
-def cost_self_collision(x, margin, sigma_self, fk_fn):
+def cost_self_collision(x, margin, sigma_self, fk_fn, num_interpolate=0, interp_range=(5, 7)):
     NP, S, T, d = x.shape
     n = d // 2
     H = fk_fn(x[:, :, 1:, :n].reshape(-1, n))
-    pos = H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3)
+    pos = interpolate_links(H[:, :, :3, 3].reshape(NP, S, T - 1, H.shape[1], 3), num_interpolate, interp_range)
     return self_rbf(pos, margin).sum(-1) * (1.0 / sigma_self ** 2)
+
+
+def cost_ee_goal(x, target_H, sigma_goal, fk_fn, w_pos=1., w_rot=1., square=True):
+    """CostGoal.eval (cost_functions.py:308-321): the field is evaluated on the LAST time step only
+    (FieldFactor range [T-1, T], cost_functions.py:300-304); EESE3DistanceField takes the last link frame as the
+    end-effector (fields.py:142-144), squares the SE(3) distance (fields.py:147-150); weight 1/sigma_goal^2."""
+    from .se3 import se3_distance
+    NP, S, T, d = x.shape
+    n = d // 2
+    H = fk_fn(x[:, :, -1, :n].reshape(-1, n))
+    dist = se3_distance(H[:, -1], np.asarray(target_H, dtype=x.dtype), w_pos, w_rot).reshape(NP, S)
+    if square:
+        dist = dist * dist
+    return dist * (1.0 / sigma_goal ** 2)
 
 
 def cost_importance(x, means, D, O, temperature):

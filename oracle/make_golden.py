@@ -33,7 +33,8 @@ def _np(t):
 
 def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_sigmas, cost_sigmas,
              temperature, step_size, iters, map_params=None, spheres=None, initial_particle_means=None,
-             sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None, field_type='rbf', clamp_sdf=False):
+             sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None, field_type='rbf', clamp_sdf=False,
+             interp=None, self_interp=None, ee_goal=None):
     ref = ref_loader.load()
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
     start_state = torch.tensor(start, **ta)
@@ -72,13 +73,21 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
     if self_field is not None:      # (margin, sigma_self): examples/panda_environment.py:67,88 — listed BEFORE the obstacle cost
         from stoch_gpmp.costs.fields import LinkSelfDistanceField
         FK = ofk.fk_all_links_torch()
-        cost_list.append(ref.CostCollision(n_dof, T, field=LinkSelfDistanceField(margin=self_field[0], tensor_args=ta),
+        skw = {}
+        if self_interp is not None:      # (num_interpolate, [lo, hi])  costs/fields.py:117-123
+            skw = dict(num_interpolate=self_interp[0], link_interpolate_range=list(self_interp[1]))
+            rec['self_num_interpolate'], rec['self_interp_range'] = self_interp[0], np.array(self_interp[1])
+        cost_list.append(ref.CostCollision(n_dof, T, field=LinkSelfDistanceField(margin=self_field[0], tensor_args=ta, **skw),
                                            sigma_coll=self_field[1]))
         term_names.append('self')
         rec['self_margin'], rec['sigma_self'] = self_field
     if spheres is not None:
         FK = ofk.fk_all_links_torch()
-        field = ref.LinkDistanceField(field_type=field_type, clamp_sdf=clamp_sdf, tensor_args=ta)
+        fkw = {}
+        if interp is not None:           # (num_interpolate, [lo, hi])  costs/fields.py:68-74
+            fkw = dict(num_interpolate=interp[0], link_interpolate_range=list(interp[1]))
+            rec['num_interpolate'], rec['interp_range'] = interp[0], np.array(interp[1])
+        field = ref.LinkDistanceField(field_type=field_type, clamp_sdf=clamp_sdf, tensor_args=ta, **fkw)
         if field_type != 'rbf':
             rec['field_type'], rec['clamp_sdf'] = field_type, clamp_sdf
         cost_list.append(ref.CostCollision(n_dof, T, field=field, sigma_coll=sigma_coll))
@@ -86,6 +95,19 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
         sph = torch.tensor(spheres, **ta).reshape(1, -1, 4)
         obs = {'obstacle_spheres': sph}
         rec['spheres'] = _np(sph[0])
+    if ee_goal is not None:
+        # CostGoal + EESE3DistanceField, last in the shipped list (examples/panda_environment.py:69,89-90); SE3_distance
+        # itself is the restatement of oracle/se3.py bound through the import stub (parity unpinned there)
+        FK = ofk.fk_all_links_torch()
+        tH = torch.tensor(ee_goal['target_H'], **ta).reshape(1, 4, 4)
+        fld = ref.EESE3DistanceField(tH, w_pos=ee_goal.get('w_pos', 1.), w_rot=ee_goal.get('w_rot', 1.),
+                                     square=ee_goal.get('square', True), tensor_args=ta)
+        cost_list.append(ref.CostGoal(n_dof, T, field=fld, sigma_goal=ee_goal['sigma_goal'], tensor_args=ta))
+        term_names.append('ee')
+        rec['ee_target'] = np.asarray(ee_goal['target_H'], dtype=np.float64).reshape(4, 4)
+        rec['sigma_ee_goal'] = ee_goal['sigma_goal']
+        rec['ee_w_pos'], rec['ee_w_rot'] = ee_goal.get('w_pos', 1.), ee_goal.get('w_rot', 1.)
+        rec['ee_square'] = ee_goal.get('square', True)
     cost = ref.CostComposite(n_dof, T, cost_list, FK=FK, tensor_args=ta)
 
     ipm = initial_particle_means
@@ -205,7 +227,25 @@ PLANAR_MAP = dict(map_dim=[20, 20], cell_size=0.1, num_obst=15, rand_limits=[[-7
 SOFT_MAP = dict(map_dim=[8, 8], cell_size=0.1, num_obst=4, rand_limits=[[-1.5, 1.5], [-1.5, 1.5]], seed=1)
 
 
-def main():
+def shipped_target_H():
+    """target frame of examples/panda_environment.py:39-43: rot = Rz(-pi) Ry(-pi), trans = (.3, .3, .3)."""
+    cz, sz = np.cos(-np.pi), np.sin(-np.pi)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    Ry = np.array([[cz, 0, sz], [0, 1, 0], [-sz, 0, cz]])
+    H = np.eye(4)
+    H[:3, :3] = Rz @ Ry
+    H[:3, 3] = [.3, .3, .3]
+    return H
+
+
+def main(only=None):
+    global run_case
+    if only:
+        _rc = run_case
+
+        def run_case(name, **kw):      # noqa: F811  (filter: regenerate only the named cases)
+            if name in only:
+                _rc(name, **kw)
     # C1-like: shipped planar sigmas (examples/planar_environment.py:52-96), fp64, small shapes
     run_case('planar_f64', n_dof=2, T=16, dt=0.02, G=3, K=2, S=6, dtype=torch.float64, seed=0,
              start=[-9, -9, 0, 0], goals=PLANAR_GOALS, planner_sigmas=PLANAR_SIGMAS,
@@ -286,5 +326,38 @@ def main():
              temperature=200., step_size=0.5, iters=2, spheres=panda_spheres(5, 1))
 
 
+    # the COMPLETE shipped Panda cost list [CostGP, CostGoalPrior, self, obstacle, CostGoal(EESE3DistanceField)]
+    # (examples/panda_environment.py:66-90, sigma_goal = 0.00007), fp64 and fp32
+    for nm, dt_ in (('panda_shipped_f64', torch.float64), ('panda_shipped_f32', torch.float32)):
+        run_case(nm, n_dof=7, T=16, dt=0.05, G=1, K=3, S=8, dtype=dt_, seed=10,
+                 start=PANDA_START, goals=panda_goals(1, 5), planner_sigmas=PANDA_SIGMAS,
+                 cost_sigmas=dict(sigma_start=0.0001, sigma_gp=0.0007), sigma_coll=0.01, sigma_goal_prior=20.,
+                 temperature=1., step_size=0.1, iters=2, spheres=panda_spheres(5, 5), self_field=(0.03, 0.01),
+                 ee_goal=dict(target_H=shipped_target_H(), sigma_goal=0.00007))
+    # soft variant with live weights, non-default w_pos / w_rot and the un-squared distance
+    tH = shipped_target_H()
+    tH[:3, 3] = [0.45, 0.1, 0.5]
+    run_case('panda_ee_soft_f64', n_dof=7, T=12, dt=0.05, G=2, K=1, S=12, dtype=torch.float64, seed=11,
+             start=PANDA_START, goals=panda_goals(2, 6),
+             planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.8,
+                                 sigma_start_sample=4.0, sigma_goal_sample=4.0, sigma_gp_sample=0.5),
+             initial_particle_means='const_vel',
+             cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
+             temperature=200., step_size=0.5, iters=1, spheres=panda_spheres(3, 6),
+             ee_goal=dict(target_H=tH, sigma_goal=0.05, w_pos=2.0, w_rot=0.5, square=False))
+    # link interpolation on both link fields (costs/fields.py:68-74, :117-123): 3 extra points between frames 5-6
+    # and 6-7 for the sphere field (the reference's default range), 2 between frames 3-4 .. 5-6 for the self field
+    for nm, dt_ in (('panda_interp_f64', torch.float64), ('panda_interp_f32', torch.float32)):
+        run_case(nm, n_dof=7, T=12, dt=0.05, G=2, K=1, S=12, dtype=dt_, seed=12,
+                 start=PANDA_START, goals=panda_goals(2, 7),
+                 planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.8,
+                                     sigma_start_sample=4.0 if dt_ == torch.float64 else 0.5,
+                                     sigma_goal_sample=4.0 if dt_ == torch.float64 else 0.5, sigma_gp_sample=0.5),
+                 initial_particle_means='const_vel',
+                 cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
+                 temperature=200., step_size=0.5, iters=1, spheres=panda_spheres(4, 7), self_field=(0.15, 0.1),
+                 interp=(3, (5, 7)), self_interp=(2, (3, 6)))
+
+
 if __name__ == '__main__':
-    main()
+    main(set(sys.argv[1:]) or None)

@@ -15,6 +15,9 @@ Reference: StochGPMP.reset / sample_and_eval / _get_costs / _update_distribution
      map [H,W], map_cell_size, map_origin (xi, yi)        ObstacleMap (envs/obst_map.py:112-147)
      spheres [O,4]                                        LinkDistanceField 'rbf' (costs/fields.py:63-79)
   self_margin, sigma_self (optional)                      LinkSelfDistanceField (costs/fields.py:89-127)
+  num_interpolate, interp_range / self_num_interpolate, self_interp_range (optional)   link interpolation (fields.py:68-74)
+  ee_target [4,4], sigma_ee_goal, ee_w_pos, ee_w_rot, ee_square (optional)   CostGoal + EESE3DistanceField
+                                                          (cost_functions.py:282-321, fields.py:130-153)
 """
 import numpy as np
 
@@ -49,6 +52,14 @@ def spec_from_golden(g):
     if 'self_margin' in g.files:
         s['self_margin'] = float(g['self_margin'])
         s['sigma_self'] = float(g['sigma_self'])
+    for pre in ('', 'self_'):
+        if pre + 'num_interpolate' in g.files:
+            s[pre + 'num_interpolate'] = int(g[pre + 'num_interpolate'])
+            s[pre + 'interp_range'] = (int(g[pre + 'interp_range'][0]), int(g[pre + 'interp_range'][1]))
+    if 'ee_target' in g.files:
+        s['ee_target'] = g['ee_target']
+        s['sigma_ee_goal'] = float(g['sigma_ee_goal'])
+        s['ee_w_pos'], s['ee_w_rot'], s['ee_square'] = float(g['ee_w_pos']), float(g['ee_w_rot']), bool(g['ee_square'])
     return s
 
 
@@ -83,7 +94,8 @@ def initial_means(spec, init_eps=None, mode=None):
 
 def eval_costs(spec, samples, means, D, O, dtype=np.float64):
     """Per-term costs [NP,S] each, and the total in the reference's summation order
-    (CostGP[start + gp], CostGoalPrior, CostCollision, then the IS term)."""
+    (CostGP[start + gp], CostGoalPrior, self-collision, obstacle collision, EE goal — the order of the shipped
+    lists, examples/panda_environment.py:90 — then the IS term)."""
     x = samples.astype(dtype)
     terms = {}
     terms['start'] = C.cost_start(x, spec['start'].astype(dtype), spec['cost_sigma_start'])
@@ -93,7 +105,8 @@ def eval_costs(spec, samples, means, D, O, dtype=np.float64):
         terms['goal'] = C.cost_goal_prior(x, spec['goals'].astype(dtype), spec['K'], spec['sigma_goal_prior'])
         total = total + terms['goal']
     if spec.get('self_margin') is not None:
-        terms['self'] = C.cost_self_collision(x, spec['self_margin'], spec['sigma_self'], lambda q: FK.fk_all_links(q))
+        terms['self'] = C.cost_self_collision(x, spec['self_margin'], spec['sigma_self'], lambda q: FK.fk_all_links(q),
+                                              spec.get('self_num_interpolate', 0), spec.get('self_interp_range', (5, 7)))
         total = total + terms['self']
     if spec.get('sigma_coll') is not None and 'map' in spec:
         terms['coll'] = C.cost_collision_map(x, spec['map'], spec['map_cell_size'], spec['map_origin'][0],
@@ -102,8 +115,13 @@ def eval_costs(spec, samples, means, D, O, dtype=np.float64):
     if spec.get('sigma_coll') is not None and 'spheres' in spec:
         terms['coll'] = C.cost_collision_spheres(x, spec['spheres'].astype(dtype), spec['sigma_coll'],
                                                  lambda q: FK.fk_all_links(q), spec.get('field_type', 'rbf'),
-                                                 spec.get('clamp_sdf', False))
+                                                 spec.get('clamp_sdf', False), spec.get('num_interpolate', 0),
+                                                 spec.get('interp_range', (5, 7)))
         total = total + terms['coll']
+    if spec.get('ee_target') is not None:
+        terms['ee'] = C.cost_ee_goal(x, spec['ee_target'], spec['sigma_ee_goal'], lambda q: FK.fk_all_links(q),
+                                     spec.get('ee_w_pos', 1.), spec.get('ee_w_rot', 1.), spec.get('ee_square', True))
+        total = total + terms['ee']
     terms['is'] = C.cost_importance(x, means.astype(dtype), D, O, spec['temperature'])
     total = total + terms['is']
     return terms, total

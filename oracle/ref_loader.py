@@ -5,7 +5,8 @@ does not exist on the GPU box, and nothing in `-m gpu` tests, smoke() or bench.p
 
 Two import stubs are needed:
   * matplotlib                — stoch_gpmp/envs/obst_map.py:4 imports pyplot only for plot()
-  * torch_robotics...SE3_distance — stoch_gpmp/costs/fields.py:4, only used by EESE3DistanceField
+  * torch_robotics...SE3_distance — stoch_gpmp/costs/fields.py:4, only used by EESE3DistanceField; bound to the
+    restatement in oracle/se3.py (parity unpinned at that function)
 """
 import os
 import sys
@@ -48,17 +49,20 @@ def load():
         for i in range(1, len(parts) + 1):
             nm = ".".join(parts[:i])
             sys.modules.setdefault(nm, types.ModuleType(nm))
-        sys.modules[tr].SE3_distance = None
+        # the absent dependency's function, restated (PARITY UNPINNED, see oracle/se3.py)
+        from .se3 import se3_distance_torch
+        sys.modules[tr].SE3_distance = se3_distance_torch
     ns = types.SimpleNamespace()
     from stoch_gpmp.planner import StochGPMP
-    from stoch_gpmp.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior
-    from stoch_gpmp.costs.fields import LinkDistanceField
+    from stoch_gpmp.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior, CostGoal
+    from stoch_gpmp.costs.fields import LinkDistanceField, LinkSelfDistanceField, EESE3DistanceField
     from stoch_gpmp.costs.factors.mp_priors_multi import MultiMPPrior
     from stoch_gpmp.envs.map_generator import generate_obstacle_map
     from stoch_gpmp.envs.obst_map import ObstacleMap, ObstacleRectangle, ObstacleCircle
     ns.StochGPMP = StochGPMP
     ns.CostCollision, ns.CostComposite, ns.CostGP, ns.CostGoalPrior = CostCollision, CostComposite, CostGP, CostGoalPrior
     ns.LinkDistanceField = LinkDistanceField
+    ns.LinkSelfDistanceField, ns.EESE3DistanceField, ns.CostGoal = LinkSelfDistanceField, EESE3DistanceField, CostGoal
     ns.MultiMPPrior = MultiMPPrior
     ns.generate_obstacle_map = generate_obstacle_map
     ns.ObstacleMap, ns.ObstacleRectangle, ns.ObstacleCircle = ObstacleMap, ObstacleRectangle, ObstacleCircle

@@ -125,8 +125,17 @@ class ReferencePort:
                 gc[i] += (eg @ self.K_goal.unsqueeze(0) @ eg.transpose(1, 2)).squeeze()
             costs = costs + gc.flatten()
         # CostCollision(LinkSelfDistanceField)   costs/fields.py:114-124
+        def interp(lt, num, rng):      # link interpolation, costs/fields.py:68-74
+            if not num:
+                return lt
+            alpha = torch.linspace(0, 1, num + 2).type_as(lt)[1:num + 1]
+            alpha = alpha.view(tuple([1] * (lt.dim() - 2) + [-1, 1]))
+            for i in range(rng[0], rng[1]):
+                X1, X2 = lt[..., i, :].unsqueeze(-2), lt[..., i + 1, :].unsqueeze(-2)
+                lt = torch.cat([lt, X1 + (X2 - X1) * alpha], dim=-2)
+            return lt
         if s.get('self_margin') is not None:
-            lt = x_trajs[:, 1:T][..., :3, -1]
+            lt = interp(x_trajs[:, 1:T][..., :3, -1], s.get('self_num_interpolate', 0), s.get('self_interp_range', (5, 7)))
             selfc = torch.exp(torch.square(lt.unsqueeze(-2) - lt.unsqueeze(-3)).sum(-1) / (-s['self_margin'] ** 2 * 2)).sum((-1, -2))
             costs = costs + (1. / s['sigma_self'] ** 2) * selfc.sum(1)
         # CostCollision
@@ -139,7 +148,7 @@ class ReferencePort:
             vals = self.map[occ[..., 1], occ[..., 0]].reshape(nb, T - 1)
             costs = costs + (1. / s['sigma_coll'] ** 2) * vals.sum(1)
         if s.get('sigma_coll') is not None and self.spheres is not None:
-            link = x_trajs[:, 1:T][..., :3, -1].unsqueeze(-2)
+            link = interp(x_trajs[:, 1:T][..., :3, -1], s.get('num_interpolate', 0), s.get('interp_range', (5, 7))).unsqueeze(-2)
             sp = self.spheres.unsqueeze(0)
             ft = s.get('field_type', 'rbf')
             if ft == 'rbf':
@@ -152,6 +161,14 @@ class ReferencePort:
             else:
                 fld = (torch.linalg.norm(link - sp[..., :3], dim=-1) < sp[..., 3]).sum((-1, -2))
             costs = costs + (1. / s['sigma_coll'] ** 2) * fld.sum(1)
+        # CostGoal(EESE3DistanceField)   cost_functions.py:308-321, fields.py:142-150 (last step, last link frame)
+        if s.get('ee_target') is not None:
+            from .se3 import se3_distance_torch
+            Ht = torch.as_tensor(s['ee_target'], dtype=self.dtype).reshape(1, 4, 4)
+            dist = se3_distance_torch(x_trajs[:, T - 1:T][..., -1, :, :], Ht, w_pos=s.get('ee_w_pos', 1.), w_rot=s.get('ee_w_rot', 1.)).squeeze()
+            if s.get('ee_square', True):
+                dist = torch.square(dist)
+            costs = costs + (1. / s['sigma_ee_goal'] ** 2) * dist.reshape(nb, 1).sum(1)
         costs = costs.reshape(self.NP, self.S)
         V = samples.reshape(-1, self.S, self.M)
         U = self.means.view(-1, 1, self.M)

@@ -13,9 +13,11 @@ TABLE_STRIDE = 16
 MAX_FRAMES = 16
 MAX_SPHERES = 16
 FIELD_RBF, FIELD_SDF, FIELD_SDF_CLAMPED, FIELD_OCCUPANCY = 0, 1, 2, 3
-NUM_TERMS = 6
-TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self")
-ABI_VERSION = 4
+MAX_INTERP = 8
+MAX_LINK_POINTS = 48
+NUM_TERMS = 7
+TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self", "ee")
+ABI_VERSION = 5
 
 
 class Shape(C.Structure):
@@ -40,6 +42,11 @@ class CostDesc(C.Structure):
         ("self_margin", C.c_double), ("self_sigma_coll", C.c_double),
         ("occ_map_u8", C.c_void_p),
         ("sphere_field_type", C.c_int32), ("reserved1", C.c_int32),
+        ("sphere_interp_n", C.c_int32), ("sphere_interp_lo", C.c_int32), ("sphere_interp_hi", C.c_int32),
+        ("self_interp_n", C.c_int32), ("self_interp_lo", C.c_int32), ("self_interp_hi", C.c_int32),
+        ("sphere_interp_alpha", C.c_double * MAX_INTERP), ("self_interp_alpha", C.c_double * MAX_INTERP),
+        ("ee_sigma_goal", C.c_double), ("ee_target_R", C.c_double * 9), ("ee_target_p", C.c_double * 3),
+        ("ee_w_pos", C.c_double), ("ee_w_rot", C.c_double), ("ee_square", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -7,6 +7,7 @@ NotImplementedError — there is no CPU fallback.
 
   CostGP          <- cost_functions.py:88-146     CostGoalPrior <- cost_functions.py:340-388
   CostCollision   <- cost_functions.py:221-261    CostComposite <- cost_functions.py:32-58
+  CostGoal        <- cost_functions.py:282-321
 """
 import ctypes as C
 
@@ -16,7 +17,7 @@ from .. import _lib
 from .. import ops
 from ..envs.occupancy import ObstacleMap
 from ..robots.serial_chain import SerialChainFK
-from .fields import LinkDistanceField, LinkSelfDistanceField
+from .fields import EESE3DistanceField, LinkDistanceField, LinkSelfDistanceField
 
 
 class Cost:
@@ -69,7 +70,7 @@ class CostGoalPrior(Cost):
 
 class CostCollision(Cost):
     """Obstacle factor over time steps 1..T-1.  field: ObstacleMap (or a list of them, one per problem of a
-    batch), LinkDistanceField('rbf') or LinkSelfDistanceField; None disables the term as in the reference."""
+    batch), LinkDistanceField or LinkSelfDistanceField; None disables the term as in the reference."""
 
     @property
     def _term(self):
@@ -83,8 +84,16 @@ class CostCollision(Cost):
 
 
 class CostGoal(Cost):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("CostGoal (EE SE(3) goal field) is outside the round-1 hot path (SURVEY §8f rank 2)")
+    """End-effector goal factor on the LAST time step (FieldFactor range [T-1, T], cost_functions.py:300-304):
+    (1/sigma_goal^2) * field.compute_cost(x_{T-1}).  field: EESE3DistanceField; None disables the term as in the
+    reference (cost_functions.py:309-310)."""
+    _term = 'ee'
+
+    def __init__(self, n_dof, traj_len, field=None, sigma_goal=None, tensor_args=None):
+        super().__init__(n_dof, traj_len)
+        self.field = field
+        self.sigma_goal = sigma_goal
+        self.tensor_args = tensor_args
 
 
 class CostGPTrajectory(Cost):
@@ -97,7 +106,7 @@ class LoweredCost:
 
     def __init__(self, composite, B, G, device, dtype):
         self.B, self.G, self.device, self.dtype = B, G, device, dtype
-        gp = goal = coll = selfc = None
+        gp = goal = coll = selfc = ee = None
         for c in composite.cost_list:
             if isinstance(c, CostGP):
                 if gp is not None:
@@ -107,6 +116,14 @@ class LoweredCost:
                 if goal is not None:
                     raise NotImplementedError("more than one CostGoalPrior in cost_list")
                 goal = c
+            elif isinstance(c, CostGoal):
+                if c.field is None:
+                    continue
+                if not isinstance(c.field, EESE3DistanceField):
+                    raise NotImplementedError("CostGoal field %s cannot be lowered to the CUDA path" % type(c.field).__name__)
+                if ee is not None:
+                    raise NotImplementedError("more than one CostGoal in cost_list")
+                ee = c
             elif isinstance(c, CostCollision):
                 if c.field is None:
                     continue                      # the reference returns 0 for a field-less collision cost
@@ -139,10 +156,19 @@ class LoweredCost:
         self.sphere_sigma = None
         self.fk = None
         self.self_margin = self.self_sigma = None
+        self.self_interp = self.sphere_interp = None          # (n, lo, hi, alpha list) when num_interpolate > 0
+        self.ee = None
         if selfc is not None:
             selfc.field.check_lowerable()
             self._need_fk(composite, n)
             self.self_margin, self.self_sigma = float(selfc.field.margin), float(selfc.sigma_coll)
+            if selfc.field.num_interpolate:
+                r = selfc.field.link_interpolate_range
+                self.self_interp = (int(selfc.field.num_interpolate), int(r[0]), int(r[1]), selfc.field.interp_alpha())
+        if ee is not None:
+            ee.field.check_lowerable()
+            self._need_fk(composite, n)
+            self.ee = (ee.field, float(ee.sigma_goal))
         if coll is not None:
             fields = coll.field if isinstance(coll.field, (list, tuple)) else [coll.field]
             if all(isinstance(f, ObstacleMap) for f in fields):
@@ -172,6 +198,9 @@ class LoweredCost:
                 self._need_fk(composite, n)
                 self.sphere_sigma = float(coll.sigma_coll)
                 self.sphere_field_type = fields[0].field_code()
+                if fields[0].num_interpolate:
+                    r = fields[0].link_interpolate_range
+                    self.sphere_interp = (int(fields[0].num_interpolate), int(r[0]), int(r[1]), fields[0].interp_alpha())
             else:
                 raise NotImplementedError("collision field %s cannot be lowered to the CUDA path"
                                           % type(fields[0]).__name__)
@@ -224,8 +253,26 @@ class LoweredCost:
                 self._fill_chain(d)
             if self.self_margin is not None:
                 d.self_margin, d.self_sigma_coll = self.self_margin, self.self_sigma
+            for pre, itp in (('self', self.self_interp), ('sphere', self.sphere_interp)):
+                if itp is not None:
+                    setattr(d, pre + '_interp_n', itp[0])
+                    setattr(d, pre + '_interp_lo', itp[1])
+                    setattr(d, pre + '_interp_hi', itp[2])
+                    arr = getattr(d, pre + '_interp_alpha')
+                    for k, a in enumerate(itp[3]):
+                        arr[k] = a
             self._desc_cache = d
         d.temperature = float(temperature)
+        if self.ee is not None:
+            # the target is re-read on every call: EESE3DistanceField.update_target (fields.py:139-140) may have moved it
+            fld, sig = self.ee
+            H = fld.target_matrix()
+            d.ee_sigma_goal = sig
+            for r in range(3):
+                for c in range(3):
+                    d.ee_target_R[3 * r + c] = float(H[r, c])
+                d.ee_target_p[r] = float(H[r, 3])
+            d.ee_w_pos, d.ee_w_rot, d.ee_square = float(fld.w_pos), float(fld.w_rot), 1 if fld.square else 0
         if self.sphere_sigma is not None:
             if obstacle_spheres is None:
                 # the reference's LinkDistanceField.compute_cost returns 0 without spheres (fields.py:64-65)

@@ -1,7 +1,24 @@
-"""Distance fields (parameter carriers).  Mirrors stoch_gpmp/costs/fields.py for the variants on the
-StochGPMP hot path: LinkDistanceField with field_type='rbf' (costs/fields.py:30-79) and
-LinkSelfDistanceField (costs/fields.py:89-127), both without link interpolation.  The arithmetic runs in
-csrc/sgpmp_cost.cuh::link_fields."""
+"""Distance fields (parameter carriers).  Mirrors stoch_gpmp/costs/fields.py: LinkDistanceField
+(costs/fields.py:30-86: 'rbf' / 'sdf' / 'occupancy', link interpolation), LinkSelfDistanceField
+(costs/fields.py:89-127) and EESE3DistanceField (costs/fields.py:130-153).  The arithmetic runs in
+csrc/sgpmp_cost.cuh (link_fields, ee_se3_cost)."""
+import torch
+
+
+def _interp_alpha(num_interpolate):
+    """alpha of costs/fields.py:69, formed exactly like the reference does: torch.linspace in the default dtype
+    (float32), then cast — the kernels receive these values as doubles (sgpmp_cost_desc_t.*_interp_alpha)."""
+    n = int(num_interpolate)
+    return [float(a) for a in torch.linspace(0, 1, n + 2)[1:n + 1].to(torch.float32)]
+
+
+def _check_interp(name, num_interpolate, rng):
+    from .. import _lib
+    n = int(num_interpolate)
+    if n < 0 or n > _lib.MAX_INTERP:
+        raise NotImplementedError("%s(num_interpolate=%d): the CUDA path supports 0..%d" % (name, n, _lib.MAX_INTERP))
+    if n and (len(rng) != 2 or rng[0] < 0 or rng[1] < rng[0]):
+        raise ValueError("%s: link_interpolate_range must be [lo, hi] with 0 <= lo <= hi, got %r" % (name, rng))
 
 
 class DistanceField:
@@ -36,8 +53,10 @@ class LinkDistanceField(DistanceField):
 
     def check_lowerable(self):
         self.field_code()
-        if self.num_interpolate:
-            raise NotImplementedError("LinkDistanceField(num_interpolate>0) is not lowered yet (SURVEY §8f rank 1)")
+        _check_interp("LinkDistanceField", self.num_interpolate, self.link_interpolate_range)
+
+    def interp_alpha(self):
+        return _interp_alpha(self.num_interpolate)
 
 
 class LinkSelfDistanceField(DistanceField):
@@ -51,10 +70,36 @@ class LinkSelfDistanceField(DistanceField):
         self.link_interpolate_range = list(link_interpolate_range)
 
     def check_lowerable(self):
-        if self.num_interpolate:
-            raise NotImplementedError("LinkSelfDistanceField(num_interpolate>0) is not lowered yet (SURVEY §8f rank 1)")
+        _check_interp("LinkSelfDistanceField", self.num_interpolate, self.link_interpolate_range)
+
+    def interp_alpha(self):
+        return _interp_alpha(self.num_interpolate)
 
 
 class EESE3DistanceField(DistanceField):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("EESE3DistanceField needs torch_robotics' SE3_distance (absent); SURVEY §8f rank 2")
+    """SE(3) distance of the end-effector (LAST link frame, costs/fields.py:142-144) to `target_H` [4,4] (or [1,4,4]),
+    squared when `square` (costs/fields.py:146-150).  The reference takes `SE3_distance` from the absent torch_robotics;
+    the CUDA path evaluates  w_pos |p - p*| + w_rot acos(clamp((tr(R^T R*) - 1)/2, -1, 1))  (csrc ee_se3_cost,
+    oracle/se3.py; parity unpinned at that one function)."""
+
+    def __init__(self, target_H, w_pos=1., w_rot=1., square=True, **kwargs):
+        super().__init__(**kwargs)
+        self.target_H = target_H
+        self.square = square
+        self.w_pos = w_pos
+        self.w_rot = w_rot
+
+    def update_target(self, target_H):
+        self.target_H = target_H
+
+    def target_matrix(self):
+        """The target as a [4,4] float64 CPU tensor (validated)."""
+        H = torch.as_tensor(self.target_H).detach().to(device='cpu', dtype=torch.float64).reshape(-1, 4, 4)
+        if H.shape[0] != 1:
+            raise NotImplementedError("EESE3DistanceField: one target pose per cost (got %d)" % H.shape[0])
+        return H[0]
+
+    def check_lowerable(self):
+        self.target_matrix()
+        if not (self.w_pos >= 0 and self.w_rot >= 0):
+            raise ValueError("EESE3DistanceField: w_pos and w_rot must be >= 0")

@@ -61,6 +61,13 @@ struct CostParams {
     int32_t joint[SGPMP_MAX_FRAMES];
     int32_t has_goal, has_map, has_spheres, has_self;
     real self_k, self_w_coll;   // self_k = -0.5/margin^2 (* log2 e in fp32)
+    // link interpolation (generic chain path only)
+    int32_t sphere_interp_n, sphere_interp_lo, sphere_interp_hi;
+    int32_t self_interp_n, self_interp_lo, self_interp_hi;
+    real sphere_alpha[SGPMP_MAX_INTERP], self_alpha[SGPMP_MAX_INTERP];
+    // EE SE(3) goal
+    int32_t has_ee, ee_square;
+    real ee_R[9], ee_p[3], ee_w_pos, ee_w_rot, ee_w;   // ee_w = 1/sigma_goal^2
 };
 
 template <typename real>

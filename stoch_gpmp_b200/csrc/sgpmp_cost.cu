@@ -59,7 +59,8 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
         set_error("cost desc: n_spheres must be <= %d and sigma_coll > 0", SGPMP_MAX_SPHERES);
         return SGPMP_ERR_INVALID_ARG;
     }
-    if (o.has_spheres || o.has_self) {
+    o.has_ee = d.ee_sigma_goal > 0;
+    if (o.has_spheres || o.has_self || o.has_ee) {
         if (o.has_map) { set_error("cost desc: link fields and an occupancy map cannot be combined"); return SGPMP_ERR_UNSUPPORTED; }
         if (d.n_frames < sh.n_dof || d.n_frames > SGPMP_MAX_FRAMES) {
             set_error("cost desc: FK chain needs n_dof <= n_frames <= %d", SGPMP_MAX_FRAMES);
@@ -95,6 +96,35 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
     if (o.has_self) {
         o.self_k = (real)((sizeof(real) == 4 ? -0.5 * 1.4426950408889634 : -0.5) / (d.self_margin * d.self_margin));
         o.self_w_coll = (real)(1.0 / (d.self_sigma_coll * d.self_sigma_coll));
+    }
+    // link interpolation: indices address the link list (base first when include_base)
+    const int L = d.n_frames + (d.include_base ? 1 : 0);
+    auto interp_ok = [&](int n, int lo, int hi, const char* which) {
+        if (n == 0) return true;
+        if (n < 0 || n > SGPMP_MAX_INTERP || lo < 0 || hi < lo || hi > L - 1 || L + n * (hi - lo) > SGPMP_MAX_LINK_POINTS) {
+            set_error("cost desc: %s interpolation needs 0 <= n <= %d, 0 <= lo <= hi <= L-1 = %d and at most %d points "
+                      "(n=%d, range [%d,%d))", which, SGPMP_MAX_INTERP, L - 1, SGPMP_MAX_LINK_POINTS, n, lo, hi);
+            return false;
+        }
+        return true;
+    };
+    if (o.has_spheres) {
+        if (!interp_ok(d.sphere_interp_n, d.sphere_interp_lo, d.sphere_interp_hi, "sphere-field")) return SGPMP_ERR_INVALID_ARG;
+        o.sphere_interp_n = d.sphere_interp_n; o.sphere_interp_lo = d.sphere_interp_lo; o.sphere_interp_hi = d.sphere_interp_hi;
+        for (int k = 0; k < d.sphere_interp_n; ++k) o.sphere_alpha[k] = (real)d.sphere_interp_alpha[k];
+    }
+    if (o.has_self) {
+        if (!interp_ok(d.self_interp_n, d.self_interp_lo, d.self_interp_hi, "self-field")) return SGPMP_ERR_INVALID_ARG;
+        o.self_interp_n = d.self_interp_n; o.self_interp_lo = d.self_interp_lo; o.self_interp_hi = d.self_interp_hi;
+        for (int k = 0; k < d.self_interp_n; ++k) o.self_alpha[k] = (real)d.self_interp_alpha[k];
+    }
+    if (o.has_ee) {
+        if (!(d.ee_w_pos >= 0) || !(d.ee_w_rot >= 0)) { set_error("cost desc: ee_w_pos / ee_w_rot must be >= 0"); return SGPMP_ERR_INVALID_ARG; }
+        for (int k = 0; k < 9; ++k) o.ee_R[k] = (real)d.ee_target_R[k];
+        for (int k = 0; k < 3; ++k) o.ee_p[k] = (real)d.ee_target_p[k];
+        o.ee_w_pos = (real)d.ee_w_pos; o.ee_w_rot = (real)d.ee_w_rot;
+        o.ee_w = (real)(1.0 / (d.ee_sigma_goal * d.ee_sigma_goal));
+        o.ee_square = d.ee_square ? 1 : 0;
     }
     return SGPMP_OK;
 }
@@ -166,6 +196,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
         terms[SGPMP_TERM_COLL * term_stride + o] = tc.c_coll;
         terms[SGPMP_TERM_IS * term_stride + o] = tc.c_is;
         terms[SGPMP_TERM_SELF * term_stride + o] = tc.c_self;
+        terms[SGPMP_TERM_EE * term_stride + o] = tc.c_ee;
     }
 }
 
@@ -240,7 +271,7 @@ static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
     if constexpr (sizeof(real) == 4) {
-        if ((P.has_spheres || P.has_self) && chain_is_panda_structure(desc, sh.n_dof))
+        if ((P.has_spheres || P.has_self) && !links_interpolated(P) && chain_is_panda_structure(desc, sh.n_dof))
             return P.has_self ? launch_cost_n<real, 7, 2>(sh, P, tables, samples, means, costs, terms, st)
                               : launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
     }

@@ -8,7 +8,8 @@
 //   CostCollision.eval      costs/cost_functions.py:247-261 + FieldFactor costs/factors/field_factor.py:18-32
 //                           (steps 1..T-1 only)
 //   ObstacleMap.get_collisions   envs/obst_map.py:164-182
-//   LinkDistanceField 'rbf'      costs/fields.py:63-79
+//   LinkDistanceField 'rbf'      costs/fields.py:63-79   (+ link interpolation :68-74)
+//   CostGoal + EESE3DistanceField   costs/cost_functions.py:282-321, costs/fields.py:130-153 (last step, last link frame)
 //   FK hook                      costs/cost_functions.py:51-52 (torch_robotics chain, restated from the URDF)
 //   IS term                      planner.py:233-236   tau * x^T Sigma^-1 mu  ==  tau * sum_t x_t . b_t, b = P mu
 #pragma once
@@ -120,6 +121,61 @@ __device__ __forceinline__ void fk_visit_links(const CostParams<typename VT<V>::
     }
 }
 
+template <typename real>
+__host__ __device__ __forceinline__ bool links_interpolated(const CostParams<real>& P) {
+    return (P.has_spheres && P.sphere_interp_n > 0) || (P.has_self && P.self_interp_n > 0);
+}
+
+__device__ __forceinline__ float sg_acos(float x) { return acosf(x); }
+__device__ __forceinline__ double sg_acos(double x) { return acos(x); }
+__device__ __forceinline__ float sg_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sg_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ void sg_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sg_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+
+// End-effector SE(3) goal cost of configuration q (CostGoal.eval cost_functions.py:308-321 over
+// EESE3DistanceField.compute_cost fields.py:146-150): pose (R, p) of the LAST frame of the chain, then
+//   dist = w_pos |p - p*| + w_rot acos(clamp((tr(R^T R*) - 1)/2, -1, 1));  cost = dist^2 (square) or dist.
+// The weight 1/sigma_goal^2 is applied by the caller.  Runs once per trajectory sample (t = T-1), so it is kept out of
+// line: the hot loop's register allocation and instruction-cache footprint do not see it.
+template <typename real, int N>
+__device__ __noinline__ real ee_se3_cost(const CostParams<real>& P, const real* q) {
+    real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+    for (int f = 0; f < P.n_frames; ++f) {
+        const real* F_ = P.R[f];
+        const real* tf = P.p[f];
+        real Rn[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            p[r] = fma(R[3 * r], tf[0], fma(R[3 * r + 1], tf[1], fma(R[3 * r + 2], tf[2], p[r])));
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                Rn[3 * r + c] = fma(R[3 * r], F_[c], fma(R[3 * r + 1], F_[3 + c], R[3 * r + 2] * F_[6 + c]));
+        }
+        if (f < N) {   // revolute z joint f: col0' = c col0 + s col1, col1' = c col1 - s col0
+            real sn, cs;
+            sg_sincos(q[f], &sn, &cs);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const real a = Rn[3 * r], b = Rn[3 * r + 1];
+                Rn[3 * r] = fma(cs, a, sn * b);
+                Rn[3 * r + 1] = fma(cs, b, -sn * a);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+    }
+    const real dx = p[0] - P.ee_p[0], dy = p[1] - P.ee_p[1], dz = p[2] - P.ee_p[2];
+    const real dpos = sg_sqrt(fma(dx, dx, fma(dy, dy, dz * dz)));
+    real tr = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tr = fma(R[k], P.ee_R[k], tr);
+    real cs = (tr - (real)1) * (real)0.5;
+    cs = cs < (real)-1 ? (real)-1 : (cs > (real)1 ? (real)1 : cs);
+    const real dist = fma(P.ee_w_pos, dpos, P.ee_w_rot * sg_acos(cs));
+    return P.ee_square ? dist * dist : dist;
+}
+
 // ---- structured chains ------------------------------------------------------------------------------
 // CHAIN = 0: generic serial arm (fk_visit_links, runtime constants).
 // CHAIN = 1 (spheres only) / 2 (+ self-collision code): "Panda structure" (7 joints): fixed rotations are
@@ -202,10 +258,10 @@ __device__ __forceinline__ void fk_panda_origins(const CostParams<typename VT<V>
 template <typename V, int N, int CHAIN = 0>
 struct TrajCost {
     using real = typename VT<V>::real;
-    V c_start, c_gp, c_goal, c_coll, c_is, c_self;
+    V c_start, c_gp, c_goal, c_coll, c_is, c_self, c_ee;
     V xp[2 * N];   // previous state
 
-    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = vbroadcast<V>((real)0); }
+    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = c_ee = vbroadcast<V>((real)0); }
 
     // Link fields of configuration q (one FK evaluation shared by both):
     //   spheres  sum_l sum_o exp(-0.5 |p_l - c_o|^2 / r_o^2)            LinkDistanceField 'rbf'   costs/fields.py:63-79
@@ -297,7 +353,40 @@ struct TrajCost {
                 }
             };
             auto fold = [&](V acc) { return (mode == SGPMP_FIELD_SDF || mode == SGPMP_FIELD_SDF_CLAMPED) ? best : acc; };
-            if (P.has_self) {
+            if (links_interpolated(P)) {
+                // link interpolation (costs/fields.py:68-74, :117-123): keep every origin, append X_i + (X_{i+1} - X_i) alpha_k
+                // for i in [lo, hi) — separately for the two fields, which carry their own (n, range)
+                V PX[SGPMP_MAX_LINK_POINTS], PY[SGPMP_MAX_LINK_POINTS], PZ[SGPMP_MAX_LINK_POINTS];
+                int L = 0;
+                fk_visit_links<V, N>(P, q, [&](V x, V y, V z) { PX[L] = x; PY[L] = y; PZ[L] = z; ++L; });
+                auto extend = [&](int n, int lo, int hi, const real* alpha) {
+                    int Lx = L;
+                    for (int i = lo; i < hi && n > 0; ++i)
+                        for (int k = 0; k < n; ++k) {
+                            PX[Lx] = PX[i] + (PX[i + 1] - PX[i]) * alpha[k];
+                            PY[Lx] = PY[i] + (PY[i + 1] - PY[i]) * alpha[k];
+                            PZ[Lx] = PZ[i] + (PZ[i + 1] - PZ[i]) * alpha[k];
+                            ++Lx;
+                        }
+                    return Lx;
+                };
+                if (P.has_spheres) {
+                    const int Lx = extend(P.sphere_interp_n, P.sphere_interp_lo, P.sphere_interp_hi, P.sphere_alpha);
+                    V acc = zero;
+                    for (int l = 0; l < Lx; ++l) spheres_at(PX[l], PY[l], PZ[l], acc);
+                    c_coll += fold(acc);
+                }
+                if (P.has_self) {
+                    const int Lx = extend(P.self_interp_n, P.self_interp_lo, P.self_interp_hi, P.self_alpha);
+                    V sa = zero;
+                    for (int l = 0; l < Lx; ++l)
+                        for (int m = l + 1; m < Lx; ++m) {
+                            const V dx = PX[l] - PX[m], dy = PY[l] - PY[m], dz = PZ[l] - PZ[m];
+                            sa += vexp2_fast(P.self_k * vfma(dx, dx, vfma(dy, dy, dz * dz)));
+                        }
+                    c_self += (real)2 * sa + (real)Lx;
+                }
+            } else if (P.has_self) {
                 // generic chain: keep every origin, then the upper triangle of the pair matrix
                 V PX[SGPMP_MAX_FRAMES + 1], PY[SGPMP_MAX_FRAMES + 1], PZ[SGPMP_MAX_FRAMES + 1];
                 int L = 0;
@@ -392,10 +481,14 @@ struct TrajCost {
         c_coll = c_coll * (P.has_map ? P.map_w_coll : P.sphere_w_coll);
         c_self = c_self * P.self_w_coll;
         c_is = (c_is + sm.mub) * P.temperature;
+        // EE SE(3) goal on the last state (xp holds x_{T-1} after the final step); scalar value types only
+        if constexpr (VT<V>::W == 1) {
+            if (P.has_ee) c_ee = ee_se3_cost<real, N>(P, xp) * P.ee_w;
+        }
     }
     // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
-    // obstacle collision (examples/panda_environment.py:90), then += IS (planner.py:236)
-    __device__ __forceinline__ V total() const { return ((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_is; }
+    // obstacle collision, EE goal (examples/panda_environment.py:90), then += IS (planner.py:236)
+    __device__ __forceinline__ V total() const { return (((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_ee) + c_is; }
 };
 
 // Per-CTA staging of the problem constants into shared memory: start [d], goal [d] of goal index g, the sphere

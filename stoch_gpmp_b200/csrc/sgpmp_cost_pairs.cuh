@@ -177,8 +177,15 @@ struct TrajCostPairs {
         coll *= (P.has_map ? P.map_w_coll : P.sphere_w_coll);
         self *= P.self_w_coll;
         const float is = (hsum(c_is) + sm.mub) * P.temperature;
+        float ee = 0.f;
+        if (P.has_ee) {     // EE SE(3) goal on the last state (xpp holds the positions of x_{T-1})
+            float q[2 * NP2];
+#pragma unroll
+            for (int k = 0; k < NP2; ++k) { q[2 * k] = lane0(xpp[k]); q[2 * k + 1] = lane1(xpp[k]); }
+            ee = ee_se3_cost<float, N>(P, q) * P.ee_w;
+        }
         if (terms6) { terms6[0] = st; terms6[1] = gp; terms6[2] = go; terms6[3] = coll; terms6[4] = is; terms6[5] = self; }
-        return ((((st + gp) + go) + self) + coll) + is;
+        return (((((st + gp) + go) + self) + coll) + ee) + is;
     }
 };
 

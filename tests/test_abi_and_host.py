@@ -133,14 +133,20 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
     ta = {'device': torch.device('cpu'), 'dtype': torch.float32}
     gp = CostGP(7, 8, torch.zeros(14), 0.05, dict(sigma_start=1., sigma_gp=1.), ta)
     with pytest.raises(NotImplementedError):
-        LinkSelfDistanceField(num_interpolate=2).check_lowerable()
+        LinkSelfDistanceField(num_interpolate=9).check_lowerable()       # more than SGPMP_MAX_INTERP
+    LinkSelfDistanceField(num_interpolate=2).check_lowerable()
     with pytest.raises(NotImplementedError, match="SerialChainFK"):
         CostComposite(7, 8, [gp, CostCollision(7, 8, field=LinkSelfDistanceField(), sigma_coll=1.)], FK=None).lower(
             1, 1, torch.device('cpu'), torch.float32)
-    with pytest.raises(NotImplementedError):
-        EESE3DistanceField(None)
-    with pytest.raises(NotImplementedError):
-        CostGoal(7, 8)
+    # CostGoal: only the EE SE(3) field lowers; one target pose; FK descriptor required
+    with pytest.raises(NotImplementedError, match="CostGoal field"):
+        CostComposite(7, 8, [gp, CostGoal(7, 8, field=LinkDistanceField(), sigma_goal=1.)]).lower(1, 1, torch.device('cpu'), torch.float32)
+    with pytest.raises(NotImplementedError, match="one target pose"):
+        EESE3DistanceField(torch.eye(4).repeat(2, 1, 1)).check_lowerable()
+    with pytest.raises(NotImplementedError, match="SerialChainFK"):
+        CostComposite(7, 8, [gp, CostGoal(7, 8, field=EESE3DistanceField(torch.eye(4)), sigma_goal=1.)], FK=None).lower(
+            1, 1, torch.device('cpu'), torch.float32)
+    CostComposite(7, 8, [gp, CostGoal(7, 8)]).lower(1, 1, torch.device('cpu'), torch.float32)    # field=None: term dropped
     # LinkDistanceField without a lowerable FK descriptor
     comp = CostComposite(7, 8, [gp, CostCollision(7, 8, field=LinkDistanceField(), sigma_coll=1.)], FK=lambda q: q)
     with pytest.raises(NotImplementedError, match="SerialChainFK"):
@@ -148,7 +154,8 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
     with pytest.raises(NotImplementedError):
         LinkDistanceField(field_type='hinge').check_lowerable()
     with pytest.raises(NotImplementedError):
-        LinkDistanceField(num_interpolate=3).check_lowerable()
+        LinkDistanceField(num_interpolate=30).check_lowerable()
+    assert LinkDistanceField(num_interpolate=3).interp_alpha() == [0.25, 0.5, 0.75]
     assert LinkDistanceField(field_type='sdf', clamp_sdf=True).field_code() == 2
     # non-square map
     om = ObstacleMap([4, 2], 0.5, tensor_args=ta)
@@ -157,6 +164,50 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
         CostComposite(2, 8, [gp2, CostCollision(2, 8, field=om, sigma_coll=1.)]).lower(1, 1, torch.device('cpu'), torch.float32)
     with pytest.raises(NotImplementedError, match="CostGP"):
         CostComposite(2, 8, []).lower(1, 1, torch.device('cpu'), torch.float32)
+
+
+def test_ee_goal_and_interpolation_reach_the_descriptor():
+    from stoch_gpmp_b200.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoal
+    from stoch_gpmp_b200.costs.fields import LinkDistanceField, LinkSelfDistanceField, EESE3DistanceField
+    from stoch_gpmp_b200.robots import PandaFK
+    ta = {'device': torch.device('cpu'), 'dtype': torch.float64}
+    gp = CostGP(7, 8, torch.zeros(14), 0.05, dict(sigma_start=1., sigma_gp=1.), ta)
+    H = torch.eye(4, dtype=torch.float64)
+    H[:3, 3] = torch.tensor([.3, .2, .1], dtype=torch.float64)
+    fld = EESE3DistanceField(H.unsqueeze(0), w_pos=2., w_rot=.5, square=False, tensor_args=ta)
+    comp = CostComposite(7, 8, [gp, CostCollision(7, 8, field=LinkSelfDistanceField(num_interpolate=2, link_interpolate_range=[3, 6]), sigma_coll=1.),
+                                CostCollision(7, 8, field=LinkDistanceField(num_interpolate=3), sigma_coll=1.),
+                                CostGoal(7, 8, field=fld, sigma_goal=0.5)], FK=PandaFK())
+    low = comp.lower(1, 1, torch.device('cpu'), torch.float64)
+    d = low.desc(1.0, torch.zeros(1, 2, 4, dtype=torch.float64))
+    assert (d.self_interp_n, d.self_interp_lo, d.self_interp_hi) == (2, 3, 6)
+    assert (d.sphere_interp_n, d.sphere_interp_lo, d.sphere_interp_hi) == (3, 5, 7)
+    assert list(d.sphere_interp_alpha)[:3] == [0.25, 0.5, 0.75]
+    assert [float(a) for a in torch.linspace(0, 1, 4)[1:3]] == list(d.self_interp_alpha)[:2]      # float32 fractions, fields.py:69
+    assert d.ee_sigma_goal == 0.5 and (d.ee_w_pos, d.ee_w_rot, d.ee_square) == (2., .5, 0)
+    assert list(d.ee_target_p) == [.3, .2, .1] and list(d.ee_target_R) == [1, 0, 0, 0, 1, 0, 0, 0, 1]
+    H2 = H.clone()
+    H2[0, 3] = 0.9
+    fld.update_target(H2)                                       # fields.py:139-140
+    assert low.desc(1.0, torch.zeros(1, 2, 4, dtype=torch.float64)).ee_target_p[0] == 0.9
+
+
+def test_interp_alpha_and_se3_oracle():
+    """oracle.costs.interp_alpha == torch.linspace(0, 1, n+2)[1:n+1] (float32, then cast: costs/fields.py:69);
+    oracle.se3: identities of the restated SE3_distance."""
+    from oracle.costs import interp_alpha
+    from oracle.se3 import se3_distance, se3_distance_torch
+    for n in range(1, 17):
+        a = torch.linspace(0, 1, n + 2)[1:n + 1]
+        assert np.array_equal(a.numpy().astype(np.float64), interp_alpha(n, np.float64))
+    H = np.eye(4)
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    H2 = np.eye(4)
+    H2[:3, :3] = [[c, -s_, 0], [s_, c, 0], [0, 0, 1]]
+    H2[:3, 3] = [3., 4., 0.]
+    assert se3_distance(H, H) == 0.0
+    assert abs(se3_distance(H2, H, 2.0, 0.5) - (2.0 * 5.0 + 0.5 * 0.7)) < 1e-12
+    assert abs(float(se3_distance_torch(torch.tensor(H2), torch.tensor(H), 2.0, 0.5)) - (10.0 + 0.35)) < 1e-12
 
 
 def test_panda_chain_from_urdf_equals_builtin():

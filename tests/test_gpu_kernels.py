@@ -53,7 +53,10 @@ def _lowered(spec, dev, dtype, B=1):
     if spec.get('self_margin') is not None:
         from stoch_gpmp_b200.costs.fields import LinkSelfDistanceField
         FK = PandaFK()
-        cl.append(CostCollision(n, T, field=LinkSelfDistanceField(margin=spec['self_margin'], tensor_args=ta), sigma_coll=spec['sigma_self']))
+        ikw = {}
+        if spec.get('self_num_interpolate'):
+            ikw = dict(num_interpolate=spec['self_num_interpolate'], link_interpolate_range=list(spec['self_interp_range']))
+        cl.append(CostCollision(n, T, field=LinkSelfDistanceField(margin=spec['self_margin'], tensor_args=ta, **ikw), sigma_coll=spec['sigma_self']))
     if 'map' in spec:
         H = spec['map'].shape[0]
         om = ObstacleMap([2, 2], 1.0, tensor_args=ta)
@@ -63,8 +66,18 @@ def _lowered(spec, dev, dtype, B=1):
         cl.append(CostCollision(n, T, field=om, sigma_coll=spec['sigma_coll']))
     if 'spheres' in spec:
         FK = PandaFK()
+        ikw = {}
+        if spec.get('num_interpolate'):
+            ikw = dict(num_interpolate=spec['num_interpolate'], link_interpolate_range=list(spec['interp_range']))
         cl.append(CostCollision(n, T, field=LinkDistanceField(field_type=spec.get('field_type', 'rbf'), clamp_sdf=spec.get('clamp_sdf', False),
-                                                              tensor_args=ta), sigma_coll=spec['sigma_coll']))
+                                                              tensor_args=ta, **ikw), sigma_coll=spec['sigma_coll']))
+    if spec.get('ee_target') is not None:
+        from stoch_gpmp_b200.costs.cost_functions import CostGoal
+        from stoch_gpmp_b200.costs.fields import EESE3DistanceField
+        FK = PandaFK()
+        fld = EESE3DistanceField(torch.tensor(spec['ee_target'], **ta).reshape(1, 4, 4), w_pos=spec['ee_w_pos'], w_rot=spec['ee_w_rot'],
+                                 square=spec['ee_square'], tensor_args=ta)
+        cl.append(CostGoal(n, T, field=fld, sigma_goal=spec['sigma_ee_goal'], tensor_args=ta))
     comp = CostComposite(n, T, cl, FK=FK, tensor_args=ta)
     G = spec['G']
     return comp, comp.lower(B, G, dev, dtype)
@@ -236,6 +249,12 @@ def test_cost_terms_match_reference(name, cuda):
                 assert rel(terms[3], g[pre + 'term_coll']) < (3e-5 if f32 else 10 * tol)
         if spec.get('self_margin') is not None:
             assert rel(terms[5], g[pre + 'term_self']) < (3e-5 if f32 else 10 * tol)
+        if spec.get('ee_target') is not None:
+            # fp32: the reference's own fp32 FK + acos carry ~1e-5 of noise on this term (the oracle test allows 1e-4)
+            assert rel(terms[6], g[pre + 'term_ee']) < (1e-4 if f32 else 10 * tol)
+            ee_o = OP.C.cost_ee_goal(g[pre + 'samples'].astype(np.float64), spec['ee_target'], spec['sigma_ee_goal'], lambda q: OFK.fk_all_links(q),
+                                     spec['ee_w_pos'], spec['ee_w_rot'], spec['ee_square'])
+            assert rel(terms[6], ee_o) < (TOL_F32 if f32 else 1e-10)
         # IS term: against the fp64 oracle everywhere; against the reference where the reference itself is
         # accurate (fp64).  The fp32 reference's IS term carries up to 4e-3 of cancellation noise.
         _, tot_o = OP.eval_costs(spec, g[pre + 'samples'].astype(np.float64), g[pre + 'means_pre'].astype(np.float64), D, O)
