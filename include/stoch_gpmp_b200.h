@@ -234,6 +234,29 @@ int sgpmp_local_stats(const sgpmp_shape_t* shape, double temperature, const void
 int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size,
                       const void* stats, void* means, void* grad, void* stream);
 
+/* Gauss-Newton GPMP (the reference's second planner, stoch_gpmp/planner.py:352-661): n_iters iterations of
+ *   A, b, K = cost.get_linear_system(means)  (cost_functions.py:60-85);  J^T J = A^T K A + damping  (planner.py:602-617);
+ *   d_theta = solve(J^T J, A^T K b)  (planner.py:619-633);  means += step_size d_theta  (planner.py:592)
+ * on the block-tridiagonal structure of J^T J (never formed densely), two launches per iteration, fp64 arithmetic.
+ *   shape      B, G, K, T, n_dof, dtype (S is ignored: GPMP draws no samples)
+ *   desc       CostGP + CostGoalPrior + link fields ('rbf' sphere field, self-collision field; with interpolation).
+ *              The occupancy map (no gradient) and the EE SE(3) goal are SGPMP_ERR_UNSUPPORTED here.
+ *   D, O       [T,3] / [T-1,4] per-DoF 2x2 blocks of the start/GP/goal part of A^T K A — the closed form of
+ *              sgpmp_prior_factor's inputs evaluated with the COST sigmas (sigma_start, sigma_gp, sigma_goal_prior)
+ *   delta, trust_region   damping: delta I, or delta diag(mean over the particles of a problem of A^T K A)
+ *   method     SGPMP_GPMP_INVERSE: d = (J^T J)^-1 g.  SGPMP_GPMP_CHOLESKY: the reference's branch AS WRITTEN
+ *              (planner.py:626-629 passes l^T with upper=False to the second triangular solve): d = diag(l)^-1 l^-1 g
+ *   means      in/out [B,NP,T,d];  d_theta optional out (last iteration);  costs out [B,NP] = b^T K b of the LAST
+ *              linear system, i.e. at the means before the last update (planner.py:545,635-637)
+ *   not_pd     out [B*NP] int32: 0, or 1 + index of the first pivot block that is not positive definite
+ *   workspace  device scratch of sgpmp_gpmp_workspace_bytes(shape, method) bytes */
+enum { SGPMP_GPMP_INVERSE = 0, SGPMP_GPMP_CHOLESKY = 1 };
+int64_t sgpmp_gpmp_workspace_bytes(const sgpmp_shape_t* shape, int32_t method);
+int sgpmp_gpmp_step(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* D, const double* O,
+                    double delta, int32_t trust_region, int32_t method, double step_size, int32_t n_iters,
+                    void* means, void* d_theta, void* costs, void* workspace, int64_t workspace_bytes,
+                    int32_t* not_pd, void* stream);
+
 /* Pipe-peak probes for the roofline denominators MEASURED_PEAKS.json lacks (bench.py times them with
  * CUDA events).  mode 0: FP32 FMA, blocks x 256 threads x iters x 128 FMA; mode 1: MUFU ex2, blocks x 256
  * threads x iters x 64 ex2.  scratch: >= 4 bytes of device memory. */

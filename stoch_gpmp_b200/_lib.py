@@ -13,6 +13,7 @@ TABLE_STRIDE = 16
 MAX_FRAMES = 16
 MAX_SPHERES = 16
 FIELD_RBF, FIELD_SDF, FIELD_SDF_CLAMPED, FIELD_OCCUPANCY = 0, 1, 2, 3
+GPMP_INVERSE, GPMP_CHOLESKY = 0, 1
 MAX_INTERP = 8
 MAX_LINK_POINTS = 48
 NUM_TERMS = 7
@@ -67,6 +68,8 @@ SIGNATURES = {
     "sgpmp_iterate": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_local_stats": (C.c_int, [_SP, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    "sgpmp_gpmp_workspace_bytes": (_i64, [_SP, _i32]),
+    "sgpmp_gpmp_step": (C.c_int, [_SP, _DP, _vp, _vp, _dbl, _i32, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "sgpmp_probe": (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
 }
 
@@ -78,7 +81,8 @@ class SgpmpError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    # $SGPMP_LIB: an alternative build of the same ABI (kernel-tuning experiments, scratch/variants.py)
+    return os.environ.get("SGPMP_LIB") or _build.LIB
 
 
 def load():

@@ -35,8 +35,8 @@ class Cost:
         return comp._eval_terms(trajs, **observation)[self._term]
 
     def get_linear_system(self, trajs, **observation):
-        raise NotImplementedError("get_linear_system belongs to the Gauss-Newton GPMP planner, which is outside the "
-                                  "StochGPMP hot path (SURVEY §8f rank 4)")
+        raise NotImplementedError("the dense (A, b, K) of cost_functions.py:60-85 is never formed here: stoch_gpmp_b200.gpmp.GPMP "
+                                  "works on the block-tridiagonal normal equations inside csrc/sgpmp_gpmp.cu")
 
 
 class CostGP(Cost):

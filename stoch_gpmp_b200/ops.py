@@ -203,3 +203,31 @@ def fk_link_positions(fk, q):
         _lib.check(lib.sgpmp_fk_link_positions(C.byref(d), n, _DT[q.dtype], q.shape[0], _ptr(q), _ptr(pos), _stream()),
                    "sgpmp_fk_link_positions")
     return pos
+
+
+_GPMP_METHODS = {'inverse': _lib.GPMP_INVERSE, 'cholesky': _lib.GPMP_CHOLESKY}
+
+
+def gpmp_step(shape, desc, D, O, means, delta, trust_region, method, step_size, n_iters=1, want_d_theta=True):
+    """n_iters Gauss-Newton GPMP iterations (planner.py:575-600) on `means` [B,NP,T,d], in place.
+    D [T,3], O [T-1,4]: float64 blocks of the start/GP/goal normal equations (planner.prior_blocks with the COST sigmas).
+    Returns (costs [B,NP] = b^T K b of the last linear system, d_theta [B,NP,T,d] of the last iteration or None)."""
+    lib = _lib.load()
+    B, NP, T, d = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof
+    _req(means, "means", None, (B, NP, T, d))
+    _req(D, "D", torch.float64, (T, 3))
+    _req(O, "O", torch.float64, (T - 1, 4))
+    if method not in _GPMP_METHODS:
+        raise NotImplementedError("solver method %r (the reference knows 'inverse' and 'cholesky', planner.py:619-633)" % (method,))
+    m = _GPMP_METHODS[method]
+    dev = means.device
+    nbytes = int(lib.sgpmp_gpmp_workspace_bytes(C.byref(shape), m))
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+    not_pd = torch.zeros(B * NP, dtype=torch.int32, device=dev)
+    costs = torch.empty(B, NP, dtype=means.dtype, device=dev)
+    d_theta = torch.empty_like(means) if want_d_theta else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sgpmp_gpmp_step(C.byref(shape), C.byref(desc), _ptr(D), _ptr(O), float(delta), 1 if trust_region else 0, m,
+                                       float(step_size), int(n_iters), _ptr(means), _ptr(d_theta), _ptr(costs), _ptr(ws),
+                                       nbytes, _ptr(not_pd), _stream()), "sgpmp_gpmp_step")
+    return costs, d_theta, not_pd

@@ -416,3 +416,11 @@ class StochGPMP(StochGPMPBatch):
         if _eps is not None:
             _eps = _eps.unsqueeze(1)             # [n_iters, 1, NP, T, d, S]
         return super().optimize(opt_iters, debug, return_samples, _eps, **observation)
+
+
+def __getattr__(name):
+    # `from stoch_gpmp.planner import GPMP` (planner.py:352) keeps working: the Gauss-Newton planner lives in gpmp.py
+    if name in ('GPMP', 'GPMPBatch'):
+        from . import gpmp
+        return getattr(gpmp, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -5,7 +5,9 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_GPMP = [g for g in _ALL if g.startswith("gpmp_")]          # runs of the reference's Gauss-Newton GPMP planner
+GOLDEN = [g for g in _ALL if not g.startswith("gpmp_")]           # runs of StochGPMP
 GOLDEN_F64 = [g for g in GOLDEN if g.endswith("f64") or g.endswith("f64_T64")]
 GOLDEN_F32 = [g for g in GOLDEN if g.endswith("f32")]
 
