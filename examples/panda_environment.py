@@ -42,7 +42,8 @@ if __name__ == '__main__':
     n_dof = panda_fk._n_dofs
     start_q = torch.tensor([0.012, -0.57, 0., -2.81, 0., 3.037, 0.741], **tensor_args)
     start_state = torch.cat((start_q, torch.zeros_like(start_q)))
-    q_goal = torch.tensor([0.9, 0.3, -0.4, -1.9, 0.2, 2.2, 0.9], **tensor_args)      # stands in for the pybullet IK solution
+    # an IK solution of the target pose (stands in for pybullet's solveInverseKinematics, examples/panda_environment.py:61)
+    q_goal = torch.tensor([-0.0138, -0.4637, 0.7626, -2.5, 0.371, 2.1212, 2.8481], **tensor_args)
     multi_goal_states = torch.cat([q_goal, torch.zeros_like(q_goal)]).unsqueeze(0)
 
     panda_self_link = LinkSelfDistanceField(margin=0.03, tensor_args=tensor_args)

@@ -239,8 +239,9 @@ int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double s
  *   d_theta = solve(J^T J, A^T K b)  (planner.py:619-633);  means += step_size d_theta  (planner.py:592)
  * on the block-tridiagonal structure of J^T J (never formed densely), two launches per iteration, fp64 arithmetic.
  *   shape      B, G, K, T, n_dof, dtype (S is ignored: GPMP draws no samples)
- *   desc       CostGP + CostGoalPrior + link fields ('rbf' sphere field, self-collision field; with interpolation).
- *              The occupancy map (no gradient) and the EE SE(3) goal are SGPMP_ERR_UNSUPPORTED here.
+ *   desc       CostGP + CostGoalPrior + link fields ('rbf' sphere field, self-collision field; with interpolation) + the EE
+ *              SE(3) goal.  The occupancy map (a floor() lookup: no gradient) and the sdf / occupancy sphere fields are
+ *              SGPMP_ERR_UNSUPPORTED here.
  *   D, O       [T,3] / [T-1,4] per-DoF 2x2 blocks of the start/GP/goal part of A^T K A — the closed form of
  *              sgpmp_prior_factor's inputs evaluated with the COST sigmas (sigma_start, sigma_gp, sigma_goal_prior)
  *   delta, trust_region   damping: delta I, or delta diag(mean over the particles of a problem of A^T K A)

@@ -26,6 +26,7 @@ from oracle import ref_loader  # noqa: E402
 from oracle import fk as ofk  # noqa: E402
 from oracle import prior as P  # noqa: E402
 from stoch_gpmp_b200.scenarios import PANDA_START, panda_goals, panda_spheres  # noqa: E402
+from oracle.make_golden import shipped_target_H  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -35,7 +36,7 @@ def _np(t):
 
 
 def run_case(name, *, n_dof, T, dt, G, K, dtype, start, goals, cost_sigmas, sigma_goal_prior, solver, step_size, iters,
-             spheres=None, sigma_coll=None, self_field=None, interp=None, mean_noise=0.05, seed=0):
+             spheres=None, sigma_coll=None, self_field=None, interp=None, ee_goal=None, mean_noise=0.05, seed=0):
     ref = ref_loader.load()
     from stoch_gpmp.planner import GPMP
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
@@ -68,6 +69,16 @@ def run_case(name, *, n_dof, T, dt, G, K, dtype, start, goals, cost_sigmas, sigm
         sph = torch.tensor(spheres, **ta).reshape(1, -1, 4)
         obs = {'obstacle_spheres': sph}
         rec['spheres'] = _np(sph[0])
+    if ee_goal is not None:     # CostGoal + EESE3DistanceField (SE3_distance = oracle/se3.py through the import stub)
+        FK = ofk.fk_all_links_torch()
+        tH = torch.tensor(ee_goal['target_H'], **ta).reshape(1, 4, 4)
+        fld = ref.EESE3DistanceField(tH, w_pos=ee_goal.get('w_pos', 1.), w_rot=ee_goal.get('w_rot', 1.),
+                                     square=ee_goal.get('square', True), tensor_args=ta)
+        cost_list.append(ref.CostGoal(n_dof, T, field=fld, sigma_goal=ee_goal['sigma_goal'], tensor_args=ta))
+        rec['ee_target'] = np.asarray(ee_goal['target_H'], dtype=np.float64).reshape(4, 4)
+        rec['sigma_ee_goal'] = ee_goal['sigma_goal']
+        rec['ee_w_pos'], rec['ee_w_rot'] = ee_goal.get('w_pos', 1.), ee_goal.get('w_rot', 1.)
+        rec['ee_square'] = ee_goal.get('square', True)
     cost = ref.CostComposite(n_dof, T, cost_list, FK=FK, tensor_args=ta)
 
     # initial particle means [G, K, T, d]: straight lines start -> goal plus a smooth perturbation (so that the GP,
@@ -125,6 +136,16 @@ def main(only=None):
                                  solver=dict(delta=1e-1, trust_region=False, method='inverse'), step_size=0.3, iters=2,
                                  spheres=panda_spheres(4, 21) + [[0.4, 0.05, 0.5, 0.2]], sigma_coll=0.1, self_field=(0.15, 0.2),
                                  interp=(2, (5, 7))),
+        # the shipped Panda cost list [CostGP, CostGoalPrior, self, spheres, CostGoal(EE SE(3))] under GPMP
+        gpmp_panda_ee_f64=dict(n_dof=7, T=12, dt=0.05, G=1, K=3, dtype=torch.float64, start=PANDA_START, goals=panda_goals(1, 22),
+                               cost_sigmas=dict(sigma_start=0.01, sigma_gp=0.3), sigma_goal_prior=0.5,
+                               solver=dict(delta=1e-2, trust_region=True, method='inverse'), step_size=0.3, iters=2,
+                               spheres=panda_spheres(3, 22), sigma_coll=0.1, self_field=(0.15, 0.2),
+                               ee_goal=dict(target_H=shipped_target_H(), sigma_goal=0.05, w_pos=1.5, w_rot=0.7)),
+        gpmp_panda_ee_nosq_f64=dict(n_dof=7, T=10, dt=0.05, G=2, K=1, dtype=torch.float64, start=PANDA_START, goals=panda_goals(2, 23),
+                                    cost_sigmas=dict(sigma_start=0.01, sigma_gp=0.3), sigma_goal_prior=0.5,
+                                    solver=dict(delta=1e-2, trust_region=False, method='cholesky'), step_size=0.3, iters=1,
+                                    ee_goal=dict(target_H=shipped_target_H(), sigma_goal=0.1, square=False)),
         # fp32 run of the first Panda case (the reference solves in fp32; compared loosely)
         gpmp_panda_f32=dict(n_dof=7, T=12, dt=0.05, G=2, K=2, dtype=torch.float32, start=PANDA_START, goals=panda_goals(2, 20),
                             cost_sigmas=dict(sigma_start=0.01, sigma_gp=0.3), sigma_goal_prior=0.5,

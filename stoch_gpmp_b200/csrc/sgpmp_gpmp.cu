@@ -36,7 +36,7 @@ struct GpmpArgs {
     const double* D;       // [T][3]   per-DoF diagonal blocks of the GP/start/goal normal equations (d11, d12, d22)
     const double* O;       // [T-1][4] per-DoF sub-diagonal blocks P[t+1,t] (o11, o12, o21, o22)
     double* gvec;          // [BP][T][d]     g = A^T K b
-    double* hvec;          // [BP][T][2][N]  sqrt(w) h of the self / sphere field rows (zero where absent)
+    double* hvec;          // [BP][T][3][N]  sqrt(w) h of the self / sphere / EE-goal rows (zero where absent)
     double* diagv;         // [BP][T][d]     diagonal of A^T K A (trust region)
     double* Lws;           // [BP][T][d][d]  Cholesky factors of the pivot blocks   (method inverse)
     double* Wws;           // [BP][T][d][d]  sub-diagonal factor blocks             (method inverse)
@@ -59,14 +59,15 @@ struct GpmpArgs {
 // link i and a F to link i+1, and for link frames  d X_l / d q_j = z_j x (X_l - o_j)  (l at or below joint j), so
 //   d c / d q_j = z_j . sum_{l below j} (X_l - o_j) x F_l     — one backward sweep over the chain.
 template <int N>
-__device__ void link_fields_grad(const CostParams<double>& P, const double* sph, const double* q,
-                                 double& c_sph, double* g_sph, double& c_self, double* g_self) {
+__device__ void link_fields_grad(const CostParams<double>& P, const double* sph, const double* q, bool want_ee,
+                                 double& c_sph, double* g_sph, double& c_self, double* g_self, double& c_ee, double* g_ee) {
     constexpr int MAXL = SGPMP_MAX_FRAMES + 1;
     double X[MAXL][3], Zax[N][3];
     const int off = P.include_base ? 1 : 0;
     const int L = P.n_frames + off;
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};          // ends as the rotation of the LAST frame (the end-effector)
     {
-        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+        double p[3] = {0, 0, 0};
         if (off) { X[0][0] = X[0][1] = X[0][2] = 0; }
         for (int f = 0; f < P.n_frames; ++f) {
             const double* F_ = P.R[f];
@@ -119,7 +120,41 @@ __device__ void link_fields_grad(const CostParams<double>& P, const double* sph,
     double F[MAXL][3];
     c_sph = 0;
     c_self = 0;
-    for (int j = 0; j < N; ++j) { g_sph[j] = 0; g_self[j] = 0; }
+    c_ee = 0;
+    for (int j = 0; j < N; ++j) { g_sph[j] = 0; g_self[j] = 0; g_ee[j] = 0; }
+    if (want_ee && P.has_ee) {
+        // EE SE(3) goal (CostGoal + EESE3DistanceField, cost_functions.py:282-337, fields.py:130-153; SE3_distance as in
+        // oracle/se3.py):  dist = w_pos |p - p*| + w_rot acos(c),  c = (tr(R^T R*) - 1)/2 clamped to [-1, 1].
+        //   d|p - p*|/dq_j = u . (z_j x (p - o_j)),  u = (p - p*)/|p - p*|
+        //   d tr(R^T R*)/dq_j = z_j . v,  v = vee(M - M^T),  M = R* R^T      (dR/dq_j = [z_j]x R)
+        //   d acos(c)/dq_j = -(1/sqrt(1 - c^2)) (1/2) z_j . v                 (zero where the clamp is active, as autograd)
+        const double* pe = X[L - 1];
+        const double dx = pe[0] - P.ee_p[0], dy = pe[1] - P.ee_p[1], dz = pe[2] - P.ee_p[2];
+        const double dpos = sqrt(dx * dx + dy * dy + dz * dz);
+        double tr = 0;
+        for (int k = 0; k < 9; ++k) tr += R[k] * P.ee_R[k];
+        double c = (tr - 1.0) * 0.5;
+        const bool clamped = !(c > -1.0 && c < 1.0);
+        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+        const double dist = P.ee_w_pos * dpos + P.ee_w_rot * acos(c);
+        // M = R* R^T ; v = (M21 - M12, M02 - M20, M10 - M01)
+        double M[9];
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                M[3 * r + cc] = P.ee_R[3 * r] * R[3 * cc] + P.ee_R[3 * r + 1] * R[3 * cc + 1] + P.ee_R[3 * r + 2] * R[3 * cc + 2];
+        const double v[3] = {M[7] - M[5], M[2] - M[6], M[3] - M[1]};
+        const double wr = clamped ? 0.0 : -P.ee_w_rot * 0.5 / sqrt(1.0 - c * c);
+        const double wp = dpos > 0 ? P.ee_w_pos / dpos : 0.0;
+        const double outer = P.ee_square ? 2.0 * dist : 1.0;
+        c_ee = P.ee_square ? dist * dist : dist;
+        for (int j = 0; j < N; ++j) {
+            const double* z = Zax[j];
+            const double* o = X[j + off];
+            const double rx = pe[0] - o[0], ry = pe[1] - o[1], rz = pe[2] - o[2];
+            const double cx = z[1] * rz - z[2] * ry, cy = z[2] * rx - z[0] * rz, cz = z[0] * ry - z[1] * rx;   // z x r
+            g_ee[j] = outer * (wp * (dx * cx + dy * cy + dz * cz) + wr * (z[0] * v[0] + z[1] * v[1] + z[2] * v[2]));
+        }
+    }
     if (P.has_spheres) {
         for (int l = 0; l < L; ++l) F[l][0] = F[l][1] = F[l][2] = 0;
         const int ni = P.sphere_interp_n, Lp = L + ni * (P.sphere_interp_hi - P.sphere_interp_lo);
@@ -200,7 +235,7 @@ gpmp_assemble_kernel(const __grid_constant__ CostParams<double> P, const __grid_
     double cost = 0.0;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         double* g = A.gvec + ((size_t)bp * T + t) * d;
-        double* hv = A.hvec + ((size_t)bp * T + t) * 2 * N;
+        double* hv = A.hvec + ((size_t)bp * T + t) * 3 * N;
         double* dg = A.diagv + ((size_t)bp * T + t) * d;
         const double* xt = x + t * d;
         double gp[N], gv[N];
@@ -243,12 +278,19 @@ gpmp_assemble_kernel(const __grid_constant__ CostParams<double> P, const __grid_
                 cost += P.inv_sig_goal2 * (e0 * e0 + e1 * e1);
             }
         }
-        double hs[N], hc[N];
+        double hs[N], hc[N], he[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) { hs[i] = 0; hc[i] = 0; }
-        if (t > 0 && (P.has_spheres || P.has_self)) {      // field rows exist for steps 1..T-1 (cost_functions.py:241-245)
-            double c_sph, c_self, g_sph[N], g_self[N];
-            link_fields_grad<N>(P, sph, xt, c_sph, g_sph, c_self, g_self);
+        for (int i = 0; i < N; ++i) { hs[i] = 0; hc[i] = 0; he[i] = 0; }
+        if (t > 0 && (P.has_spheres || P.has_self || (P.has_ee && t == T - 1))) {
+            // field rows exist for steps 1..T-1 (cost_functions.py:241-245), the EE-goal row for T-1 only (:300-304)
+            double c_sph, c_self, c_ee, g_sph[N], g_self[N], g_ee[N];
+            link_fields_grad<N>(P, sph, xt, t == T - 1, c_sph, g_sph, c_self, g_self, c_ee, g_ee);
+            if (P.has_ee && t == T - 1) {
+                const double w = P.ee_w;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { gp[i] += w * (-g_ee[i]) * c_ee; he[i] = sqrt(w) * (-g_ee[i]); }
+                cost += w * c_ee * c_ee;
+            }
             if (P.has_spheres) {
                 const double w = P.sphere_w_coll;
 #pragma unroll
@@ -266,8 +308,8 @@ gpmp_assemble_kernel(const __grid_constant__ CostParams<double> P, const __grid_
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             g[i] = gp[i]; g[N + i] = gv[i];
-            hv[i] = hs[i]; hv[N + i] = hc[i];
-            dg[i] = Dt[0] + hs[i] * hs[i] + hc[i] * hc[i];
+            hv[i] = hs[i]; hv[N + i] = hc[i]; hv[2 * N + i] = he[i];
+            dg[i] = Dt[0] + hs[i] * hs[i] + hc[i] * hc[i] + he[i] * he[i];
             dg[N + i] = Dt[2];
         }
     }
@@ -305,7 +347,7 @@ gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
     int bad = 0;
     for (int t = 0; t < T; ++t) {
         const double* Dt = A.D + 3 * t;
-        const double* hv = A.hvec + ((size_t)bp * T + t) * 2 * N;
+        const double* hv = A.hvec + ((size_t)bp * T + t) * 3 * N;
         // ---- pivot block S = D_t + sum_f h_f h_f^T + damping - W_{t-1} W_{t-1}^T -----------------------------------
         if (row) {
             double damp = A.delta;
@@ -318,7 +360,7 @@ gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
                 const int ak = k / N, kk = k - ak * N;
                 double v = 0;
                 if (ii == kk) v = (ai == 0 && ak == 0) ? Dt[0] : ((ai == 1 && ak == 1) ? Dt[2] : Dt[1]);
-                if (ai == 0 && ak == 0) v += hv[ii] * hv[kk] + hv[N + ii] * hv[N + kk];
+                if (ai == 0 && ak == 0) v += hv[ii] * hv[kk] + hv[N + ii] * hv[N + kk] + hv[2 * N + ii] * hv[2 * N + kk];
                 if (k == i) v += damp;
                 if (t > 0) {
                     double acc = 0;
@@ -446,7 +488,7 @@ static size_t gpmp_ws_doubles(const sgpmp_shape_t& sh, int method, size_t* offs 
     const size_t BP = (size_t)sh.B * sh.G * sh.K, T = sh.T, d = 2 * (size_t)sh.n_dof;
     size_t o = 0;
     offs[0] = o; o += BP * T * d;              // gvec
-    offs[1] = o; o += BP * T * d;              // hvec (2 N = d)
+    offs[1] = o; o += BP * T * (3 * d / 2);    // hvec (3 N)
     offs[2] = o; o += BP * T * d;              // diagv
     offs[3] = o; if (method == GPMP_METHOD_INVERSE) o += BP * T * d * d;   // Lws
     offs[4] = o; if (method == GPMP_METHOD_INVERSE) o += BP * T * d * d;   // Wws
@@ -466,7 +508,6 @@ static int launch_gpmp(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
                   "reference's GPMP cannot differentiate it either (field_factor.py:35)");
         return SGPMP_ERR_UNSUPPORTED;
     }
-    if (P.has_ee) { set_error("sgpmp_gpmp_step: the EE SE(3) goal rows are not lowered for GPMP"); return SGPMP_ERR_UNSUPPORTED; }
     if (P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF) {
         set_error("sgpmp_gpmp_step: only the 'rbf' sphere field is differentiated");
         return SGPMP_ERR_UNSUPPORTED;

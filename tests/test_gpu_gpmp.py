@@ -37,6 +37,13 @@ def _planner(spec, dev, dtype, means, batch=None):
         if spec.get('num_interpolate'):
             ikw = dict(num_interpolate=spec['num_interpolate'], link_interpolate_range=list(spec['interp_range']))
         cl.append(CostCollision(n, T, field=LinkDistanceField(tensor_args=ta, **ikw), sigma_coll=spec['sigma_coll']))
+    if spec.get('ee_target') is not None:
+        from stoch_gpmp_b200.costs.cost_functions import CostGoal
+        from stoch_gpmp_b200.costs.fields import EESE3DistanceField
+        FK = PandaFK()
+        fld = EESE3DistanceField(torch.tensor(spec['ee_target'], **ta).reshape(1, 4, 4), w_pos=spec['ee_w_pos'], w_rot=spec['ee_w_rot'],
+                                 square=spec['ee_square'], tensor_args=ta)
+        cl.append(CostGoal(n, T, field=fld, sigma_goal=spec['sigma_ee_goal'], tensor_args=ta))
     comp = CostComposite(n, T, cl, FK=FK, tensor_args=ta)
     cls = GPMPBatch if batch else GPMP
     return cls(num_particles_per_goal=spec['K'], traj_len=T, opt_iters=1, dt=spec['dt'], n_dof=n, step_size=spec['step_size'],
