@@ -259,9 +259,11 @@ template <typename V, int N, int CHAIN = 0>
 struct TrajCost {
     using real = typename VT<V>::real;
     V c_start, c_gp, c_goal, c_coll, c_is, c_self, c_ee;
+    V map_pending; // occupancy value gathered at the previous step, not yet accumulated (hides the gather latency)
+    unsigned map_pending_u8;   // byte-map form of it: the RAW byte, converted when consumed (scalar value types)
     V xp[2 * N];   // previous state
 
-    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = c_ee = vbroadcast<V>((real)0); }
+    __device__ __forceinline__ void begin() { c_start = c_gp = c_goal = c_coll = c_is = c_self = c_ee = map_pending = vbroadcast<V>((real)0); map_pending_u8 = 0u; }
 
     // Link fields of configuration q (one FK evaluation shared by both):
     //   spheres  sum_l sum_o exp(-0.5 |p_l - c_o|^2 / r_o^2)            LinkDistanceField 'rbf'   costs/fields.py:63-79
@@ -413,14 +415,18 @@ struct TrajCost {
 
     // X*(1/cell) + offset with two roundings, floor, int, clamp; value = map[iy][ix].  The reference clamps ix
     // with shape[0] and iy with shape[1] (obst_map.py:177-178); maps are square here.
-    __device__ __forceinline__ real map_value1(const CostParams<real>& P, const CostSmem<real>& sm, real x, real y) const {
+    __device__ __forceinline__ int map_index(const CostParams<real>& P, real x, real y) const {
         const real xo = sg_mul_add_2r(x, P.map_inv_cell, P.map_origin_x);
         const real yo = sg_mul_add_2r(y, P.map_inv_cell, P.map_origin_y);
         int ix = (int)sg_floor(xo), iy = (int)sg_floor(yo);
         ix = min(max(ix, 0), P.map_h - 1);
         iy = min(max(iy, 0), P.map_w - 1);
-        if (sm.map_u8) return (real)__ldg(sm.map_u8 + (size_t)iy * P.map_w + ix);
-        return __ldg(sm.map + (size_t)iy * P.map_w + ix);
+        return iy * P.map_w + ix;
+    }
+    __device__ __forceinline__ real map_value1(const CostParams<real>& P, const CostSmem<real>& sm, real x, real y) const {
+        const int idx = map_index(P, x, y);
+        if (sm.map_u8) return (real)__ldg(sm.map_u8 + idx);
+        return __ldg(sm.map + idx);
     }
     __device__ __forceinline__ V map_value(const CostParams<real>& P, const CostSmem<real>& sm, V x, V y) const {
         if constexpr (VT<V>::W == 2) {
@@ -449,7 +455,21 @@ struct TrajCost {
                 c_gp = vfma(ep, vfma(P.q12x2, ev, P.q11 * ep), c_gp);
                 c_gp = vfma(P.q22 * ev, ev, c_gp);
             }
-            if (P.has_map) c_coll += map_value(P, sm, x[0], x[1]);
+            if (P.has_map) {
+                // consume the gather of the PREVIOUS step, issue this step's (integer counts: exact in any order)
+                if constexpr (VT<V>::W == 1) {
+                    if (sm.map_u8) {
+                        c_coll += (real)map_pending_u8;
+                        map_pending_u8 = __ldg(sm.map_u8 + map_index(P, x[0], x[1]));
+                    } else {
+                        c_coll += map_pending;
+                        map_pending = __ldg(sm.map + map_index(P, x[0], x[1]));
+                    }
+                } else {
+                    c_coll += map_pending;
+                    map_pending = map_value(P, sm, x[0], x[1]);
+                }
+            }
             if (P.has_spheres || P.has_self) link_fields(P, sm, x);
         }
         if (t == T - 1 && P.has_goal) {
@@ -472,6 +492,10 @@ struct TrajCost {
     }
 
     __device__ __forceinline__ void finish(const CostParams<real>& P, const CostSmem<real>& sm, int T) {
+        if (P.has_map) {
+            c_coll += map_pending;
+            if constexpr (VT<V>::W == 1) c_coll += (real)map_pending_u8;
+        }
         c_start = c_start * P.inv_sig_start2;
         c_goal = c_goal * P.inv_sig_goal2;
         if (CHAIN >= 1) {

@@ -25,11 +25,14 @@ struct TrajCostPairs {
     F2 c_start, c_gp, c_goal, c_is;                // per-lane partial sums over DoFs (summed horizontally at the end)
     F2 a01, a23, a45;                              // sphere-field sums of the link pairs (weights (1,1) (2,1) (2,1))
     float c_coll, c_self;                          // scalar accumulators (map lookups, self field, generic chains)
+    float map_pending;                             // occupancy value gathered at the previous step, not yet accumulated
+    unsigned map_pending_u8;                       // same for the byte map: the RAW byte (converted when consumed)
     F2 xpp[NP2], xpv[NP2];                         // previous state
 
     __device__ __forceinline__ void begin() {
         c_start = c_gp = c_goal = c_is = a01 = a23 = a45 = f2(0.f, 0.f);
-        c_coll = c_self = 0.f;
+        c_coll = c_self = map_pending = 0.f;
+        map_pending_u8 = 0u;
     }
 
     // Panda structure (see fk_panda_origins): sin/cos of the three joint PAIRS packed, scalar chain, link pairs packed.
@@ -115,14 +118,24 @@ struct TrajCostPairs {
         }
     }
 
-    __device__ __forceinline__ float map_value1(const CostParams<float>& P, const CostSmem<float>& sm, float x, float y) const {
+    // Issues the gather of this step and accumulates the one of the PREVIOUS step: nothing in this step depends on the
+    // load (not even the byte -> float conversion), so its L1/L2 latency hides behind the next step's RNG and recurrence
+    // (ncu: the gather's consumer carried 23 % of the planar kernel's stall samples).  Occupancy sums are small integers,
+    // exact in any order: bit-identical to the in-order sum.
+    __device__ __forceinline__ void map_gather_deferred(const CostParams<float>& P, const CostSmem<float>& sm, float x, float y) {
         const float xo = sg_mul_add_2r(x, P.map_inv_cell, P.map_origin_x);
         const float yo = sg_mul_add_2r(y, P.map_inv_cell, P.map_origin_y);
         int ix = (int)floorf(xo), iy = (int)floorf(yo);
         ix = min(max(ix, 0), P.map_h - 1);
         iy = min(max(iy, 0), P.map_w - 1);
-        if (sm.map_u8) return (float)__ldg(sm.map_u8 + (size_t)iy * P.map_w + ix);
-        return __ldg(sm.map + (size_t)iy * P.map_w + ix);
+        const int idx = iy * P.map_w + ix;
+        if (sm.map_u8) {
+            c_coll += (float)map_pending_u8;
+            map_pending_u8 = __ldg(sm.map_u8 + idx);
+        } else {
+            c_coll += map_pending;
+            map_pending = __ldg(sm.map + idx);
+        }
     }
 
     // feed state x_t as DoF pairs: xp[k] = (pos_2k, pos_2k+1), xv[k] = (vel_2k, vel_2k+1)
@@ -146,7 +159,7 @@ struct TrajCostPairs {
                 c_gp = vfma(ep, vfma(P.q12x2, ev, P.q11 * ep), c_gp);
                 c_gp = vfma(P.q22 * ev, ev, c_gp);
             }
-            if (P.has_map) c_coll += map_value1(P, sm, lane0(xp[0]), lane1(xp[0]));
+            if (P.has_map) map_gather_deferred(P, sm, lane0(xp[0]), lane1(xp[0]));
             if (CHAIN >= 1 && (P.has_spheres || P.has_self)) link_fields(P, sm, xp);
         }
         if (t == T - 1 && P.has_goal) {
@@ -168,7 +181,7 @@ struct TrajCostPairs {
         const float st = hsum(c_start) * P.inv_sig_start2;
         const float gp = hsum(c_gp);
         const float go = hsum(c_goal) * P.inv_sig_goal2;
-        float coll = c_coll, self = c_self;
+        float coll = (c_coll + map_pending) + (float)map_pending_u8, self = c_self;
         if (CHAIN >= 1) {
             coll += (hsum(a01) + (2.f * lane0(a23) + lane1(a23))) + (2.f * lane0(a45) + lane1(a45));
             coll += (float)(T - 1) * sm.coll_const;
