@@ -177,21 +177,13 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     TrajCost<real, N, CHAIN> tc;
     tc.begin();
     const real* xs = samples + (size_t)bp * T * d * S + s;
-    // the state of step t+1 is loaded before step t is evaluated (register double buffer): one thread marches over t, so
-    // without it every step would expose a full HBM round trip
-    real xn[d];
-#pragma unroll
-    for (int j = 0; j < d; ++j) xn[j] = xs[(size_t)j * S];
     for (int t = 0; t < T; ++t) {
         real x[d], y[d];
 #pragma unroll
-        for (int j = 0; j < d; ++j) x[j] = xn[j];
-        if (t + 1 < T) {
-#pragma unroll
-            for (int j = 0; j < d; ++j) xn[j] = xs[((size_t)(t + 1) * d + j) * S];
+        for (int j = 0; j < d; ++j) {
+            x[j] = xs[((size_t)t * d + j) * S];
+            y[j] = means ? x[j] - mu[t * d + j] : x[j];
         }
-#pragma unroll
-        for (int j = 0; j < d; ++j) y[j] = means ? x[j] - mu[t * d + j] : x[j];
         tc.step(P, sm, t, T, x, y, y + N, means ? bvec + t * DP : nullptr);
     }
     tc.finish(P, sm, T);

@@ -33,8 +33,12 @@
 #ifndef SGPMP_MINB_PACKED
 #define SGPMP_MINB_PACKED 2
 #endif
+#ifndef SGPMP_T_UNROLL
+#define SGPMP_T_UNROLL 1      // unroll factor of the dof-pair time loop (tuning aid; 2 was measured slower)
+#endif
 
 namespace cg = cooperative_groups;
+constexpr int SGPMP_T_UNROLL_C = SGPMP_T_UNROLL;
 
 namespace sgpmp {
 
@@ -148,7 +152,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 F2 yp[NP2], yv[NP2], enp[NP2], env[NP2];
 #pragma unroll
                 for (int k = 0; k < NP2; ++k) yp[k] = yv[k] = f2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll SGPMP_T_UNROLL_C
                 for (int t = 0; t < T; ++t) {
                     F2 ep[NP2], ev[NP2];
                     if (eps) {
