@@ -507,7 +507,12 @@ struct TrajCost {
         c_is = (c_is + sm.mub) * P.temperature;
         // EE SE(3) goal on the last state (xp holds x_{T-1} after the final step); scalar value types only
         if constexpr (VT<V>::W == 1) {
-            if (P.has_ee) c_ee = ee_se3_cost<real, N>(P, xp) * P.ee_w;
+            if (P.has_ee) {
+                real q[N];      // a COPY: taking the address of xp itself would demote the whole previous-state array to local memory
+#pragma unroll
+                for (int i = 0; i < N; ++i) q[i] = xp[i];
+                c_ee = ee_se3_cost<real, N>(P, q) * P.ee_w;
+            }
         }
     }
     // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
