@@ -271,7 +271,7 @@ static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
     if constexpr (sizeof(real) == 4) {
-        if ((P.has_spheres || P.has_self) && !links_interpolated(P) && chain_is_panda_structure(desc, sh.n_dof))
+        if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof))
             return P.has_self ? launch_cost_n<real, 7, 2>(sh, P, tables, samples, means, costs, terms, st)
                               : launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
     }

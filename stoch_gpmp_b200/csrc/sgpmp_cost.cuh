@@ -125,6 +125,11 @@ template <typename real>
 __host__ __device__ __forceinline__ bool links_interpolated(const CostParams<real>& P) {
     return (P.has_spheres && P.sphere_interp_n > 0) || (P.has_self && P.self_interp_n > 0);
 }
+// true when the link fields can run on the structured Panda code (CHAIN >= 1): RBF sphere field, no interpolation
+template <typename real>
+inline bool structured_fields_ok(const CostParams<real>& P) {
+    return (P.has_spheres || P.has_self) && !links_interpolated(P) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
+}
 
 __device__ __forceinline__ float sg_acos(float x) { return acosf(x); }
 __device__ __forceinline__ double sg_acos(double x) { return acos(x); }
@@ -278,27 +283,9 @@ struct TrajCost {
             fk_panda_origins<V>(P, q, X, Y, Z);
 #pragma unroll
             for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = vfma(X[l], X[l], vfma(Y[l], Y[l], Z[l] * Z[l]));
-            if (P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF) {
-                // sdf / occupancy variants (costs/fields.py:80-86) over ALL 11 frames: the 6 evaluated origins (weights
-                // {1,1,2,1,2,1} matter for the occupancy count only) plus the q-independent base / link1 / link2 origins
-                const real z0 = P.p[0][2];
-                V best = vbroadcast<V>((real)-1e30), cnt = zero;
-                for (int o = 0; o < O; ++o) {
-                    const real* s = sm.sph + SPH_STRIDE * o;
-                    const real cx = s[0], cy = s[1], cz = s[2], r = s[3];
-                    auto one = [&](V x, V y, V z, real w) {
-                        const V dx = x - cx, dy = y - cy, dz = z - cz;
-                        const V sd = r - vsqrt(vfma(dx, dx, vfma(dy, dy, dz * dz)));
-                        best = vmaxv(best, P.sphere_mode == SGPMP_FIELD_SDF_CLAMPED ? vminv(sd, zero) : sd);
-                        cnt = cnt + w * vstep_pos(sd);
-                    };
-#pragma unroll
-                    for (int l = 0; l < PANDA_EVAL_LINKS; ++l) one(X[l], Y[l], Z[l], (l == 2 || l == 4) ? (real)2 : (real)1);
-                    if (P.include_base) one(zero, zero, zero, (real)1);
-                    one(zero, zero, vbroadcast<V>(z0), (real)2);
-                }
-                c_coll += (P.sphere_mode == SGPMP_FIELD_OCCUPANCY) ? cnt : best;
-            } else if (P.has_spheres) {
+            // (the sdf / occupancy variants of the sphere field, costs/fields.py:80-86, always take the generic chain code:
+            // keeping them out of this path keeps its register footprint at that of the RBF field)
+            if (P.has_spheres) {
                 V acc = zero, acc2 = zero;   // acc2: links with weight 2
                 for (int o = 0; o < O; ++o) {
                     const real* s = sm.sph + SPH_STRIDE * o;

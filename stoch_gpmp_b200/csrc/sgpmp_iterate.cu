@@ -503,7 +503,7 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     A.means = (real*)means; A.means_pre = (real*)means_pre; A.samples = (real*)samples;
     A.costs = (real*)costs; A.weights = (real*)weights; A.grad = (real*)grad;
     if constexpr (sizeof(real) == 4) {
-        if ((P.has_spheres || P.has_self) && !links_interpolated(P) && chain_is_panda_structure(desc, sh.n_dof))
+        if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof))
             return P.has_self ? launch_iterate_n<real, 7, 2>(sh, P, A, st) : launch_iterate_n<real, 7, 1>(sh, P, A, st);
     }
     switch (sh.n_dof) {
