@@ -258,6 +258,15 @@ int sgpmp_gpmp_step(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, c
                     void* means, void* d_theta, void* costs, void* workspace, int64_t workspace_bytes,
                     int32_t* not_pd, void* stream);
 
+/* Weighted sample covariance of every particle (diagnostic; NO reference counterpart — the reference keeps Sigma^-1 fixed,
+ * planner.py:226; asked for by the north-star next to the weighted-mean update of planner.py:263-275):
+ *   cov[b,p] = sum_s w[b,p,s] (x_s - mu)(x_s - mu)^T      samples [B,NP,T,d,S] (S-minor), means [B,NP,T,d], weights [B,NP,S]
+ *   cov out  [B,NP,M,M], M = T*d.
+ * fp32 with use_tensor_cores != 0: tcgen05.mma kind::tf32 with a 3xTF32 split (accumulator in TMEM); otherwise (and always
+ * for fp64) a CUDA-core kernel with fp64 accumulation.  B*NP <= 65535. */
+int sgpmp_weighted_cov(const sgpmp_shape_t* shape, const void* samples, const void* means, const void* weights,
+                       void* cov, int32_t use_tensor_cores, void* stream);
+
 /* Pipe-peak probes for the roofline denominators MEASURED_PEAKS.json lacks (bench.py times them with
  * CUDA events).  mode 0: FP32 FMA, blocks x 256 threads x iters x 128 FMA; mode 1: MUFU ex2, blocks x 256
  * threads x iters x 64 ex2.  scratch: >= 4 bytes of device memory. */

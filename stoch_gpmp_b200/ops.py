@@ -231,3 +231,22 @@ def gpmp_step(shape, desc, D, O, means, delta, trust_region, method, step_size, 
                                        float(step_size), int(n_iters), _ptr(means), _ptr(d_theta), _ptr(costs), _ptr(ws),
                                        nbytes, _ptr(not_pd), _stream()), "sgpmp_gpmp_step")
     return costs, d_theta, not_pd
+
+
+def weighted_cov(shape, samples, means, weights, tensor_cores=True):
+    """cov[b,p] = sum_s w_s (x_s - mu)(x_s - mu)^T  ->  [B,NP,M,M].  fp32 runs on the tensor cores (tcgen05, 3xTF32) unless
+    tensor_cores=False; fp64 always on the CUDA cores.  No reference counterpart (diagnostic)."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    dt = samples.dtype
+    _req(samples, "samples", None, (B, NP, T, d, S))
+    _req(means, "means", dt, (B, NP, T, d))
+    _req(weights, "weights", dt, (B, NP, S))
+    M = T * d
+    if B * NP * M * M * samples.element_size() > 32 * 2 ** 30:
+        raise ValueError("weighted_cov: the [B,NP,M,M] output would take %.1f GiB" % (B * NP * M * M * samples.element_size() / 2 ** 30))
+    cov = torch.empty(B, NP, M, M, dtype=dt, device=samples.device)
+    with torch.cuda.device(samples.device):
+        _lib.check(lib.sgpmp_weighted_cov(C.byref(shape), _ptr(samples), _ptr(means), _ptr(weights), _ptr(cov),
+                                          1 if tensor_cores else 0, _stream()), "sgpmp_weighted_cov")
+    return cov

@@ -377,6 +377,18 @@ class StochGPMPBatch:
             ss = xs.permute(0, 1, 4, 2, 3)
         return self._out(ss[..., :n]).detach().clone(), self._out(ss[..., -n:]).detach().clone()
 
+    def weighted_covariance(self, tensor_cores=True):
+        """Diagnostic with no reference counterpart (the reference keeps Sigma^-1 fixed, planner.py:226): the weighted sample
+        covariance  sum_s w_s (x_s - mu)(x_s - mu)^T  [NP, M, M] of the LAST optimize() iteration, with the weights and the
+        pre-update means of that iteration.  fp32: tcgen05 tensor-core kernel (csrc/sgpmp_cov.cu)."""
+        if self._last is None:
+            raise AttributeError("optimize() has not been called yet")
+        xs = self._last['samples']
+        if xs is None:
+            xs = ops.sample(self._shape(), self._tables, self._last['means_pre'], eps_in=self._last['eps'], seed=self.seed,
+                            draw=self._last['draw'])
+        return self._out(ops.weighted_cov(self._shape(), xs, self._last['means_pre'], self._weights_raw.contiguous(), tensor_cores))
+
     def sample_trajectories(self, num_samples_per_particle):
         """planner.py:339-348."""
         n = self.n_dof

@@ -666,3 +666,52 @@ def test_cluster_sizes_agree_with_one_problem_at_a_time(B, S, cuda):
         mu_b, c_b = run(b, b + 1)
         assert float((c_all[b] - c_b[0]).abs().max() / c_b.abs().max()) < 1e-5
         assert float((mu_all[b] - mu_b[0]).abs().max() / mu_b.abs().max()) < 1e-3       # fp32 softmax sensitivity
+
+
+# ------------------------------------------------------------------------ weighted covariance (tensor cores)
+@pytest.mark.parametrize("n,T,S,NP", [(7, 64, 512, 2), (2, 64, 256, 3), (7, 10, 40, 2), (3, 7, 33, 1)])
+def test_weighted_cov_tensor_cores(n, T, S, NP, cuda):
+    """sum_s w_s (x_s - mu)(x_s - mu)^T on tcgen05 (3xTF32) against numpy fp64 and the fp64 CUDA-core kernel.  No reference
+    counterpart (diagnostic); full tiles (M = 896), two-tile, and ragged M / S (M = 140, 42; S = 40, 33)."""
+    rs = np.random.RandomState(n * 100 + T)
+    d = 2 * n
+    M = T * d
+    mu = rs.normal(0, 1.0, (1, NP, T, d))
+    x = mu[..., None] + rs.normal(0, 0.3, (1, NP, T, d, S)) * rs.uniform(0.2, 2.0, (1, NP, T, d, 1))
+    w = rs.dirichlet(np.ones(S) * 0.3, (1, NP))
+    Y = (x - mu[..., None]).reshape(NP, M, S)
+    want = np.einsum('pis,ps,pjs->pij', Y, w[0], Y)
+    sh = _ops().make_shape(1, NP, 1, S, T, n, torch.float32)
+    xs, mt, wt = (torch.tensor(a, device=cuda, dtype=torch.float32) for a in (x, mu, w))
+    Yf = (xs.double() - mt.double().unsqueeze(-1)).reshape(NP, M, S).cpu().numpy()         # the fp32 inputs, exactly
+    want32 = np.einsum('pis,ps,pjs->pij', Yf, wt.double().cpu().numpy()[0], Yf)
+    got = _ops().weighted_cov(sh, xs, mt, wt, tensor_cores=True).cpu().numpy()[0]
+    assert got.shape == (NP, M, M)
+    assert rel(got, want32) < 1e-5                   # 3xTF32 + tensor-core fp32 accumulation: 5e-6 measured (plain TF32: ~5e-4)
+    assert rel(got, np.transpose(got, (0, 2, 1))) < 1e-5
+    simple = _ops().weighted_cov(sh, xs, mt, wt, tensor_cores=False).cpu().numpy()[0]
+    assert rel(simple, want32) < 1e-6
+    sh64 = _ops().make_shape(1, NP, 1, S, T, n, torch.float64)
+    got64 = _ops().weighted_cov(sh64, xs.double(), mt.double(), wt.double()).cpu().numpy()[0]
+    assert rel(got64, want32) < 1e-13
+    assert rel(want32, want) < 1e-5
+
+
+def test_planner_weighted_covariance(cuda):
+    g = load('panda_soft_f32')
+    spec = OP.spec_from_golden(g)
+    from stoch_gpmp_b200.planner import StochGPMP
+    ta = dict(device=cuda, dtype=torch.float32)
+    comp, _ = _lowered(spec, cuda, torch.float32)
+    pl = StochGPMP(num_particles_per_goal=spec['K'], num_samples=spec['S'], traj_len=spec['T'], opt_iters=1, dt=spec['dt'], n_dof=spec['n_dof'],
+                   step_size=spec['step_size'], temperature=spec['temperature'], start_state=torch.tensor(spec['start'], **ta),
+                   multi_goal_states=torch.tensor(spec['goals'], **ta), initial_particle_means='const_vel', cost=comp, seed=3, tensor_args=ta,
+                   **{k: spec[k] for k in ('sigma_start_init', 'sigma_gp_init', 'sigma_goal_init', 'sigma_start_sample', 'sigma_gp_sample', 'sigma_goal_sample')})
+    pm, vm, ps, vs, costs, grad = pl.optimize(return_samples=True, **_obs(spec, cuda, torch.float32))
+    cov = pl.weighted_covariance().cpu().numpy().astype(np.float64)
+    x = torch.cat([ps, vs], -1).double().cpu().numpy()                         # [NP,S,T,d]
+    mu = torch.cat([pm, vm], -1).double().cpu().numpy()                        # [NP,T,d] (pre-update means)
+    w = pl._weights.reshape(pl.num_particles, -1).double().cpu().numpy()
+    Y = (x - mu[:, None]).reshape(x.shape[0], x.shape[1], -1)
+    want = np.einsum('psi,ps,psj->pij', Y, w, Y)
+    assert rel(cov, want) < 2e-5
