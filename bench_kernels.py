@@ -104,6 +104,26 @@ def main():
         ops.local_stats(sh, w["temperature"], costs, eps)
     report("local_stats (split mode)", timeit(k_stats), bytes_=ntraj * (M + 1) * 4)
 
+    # weighted covariance diagnostic (tcgen05): the first Bc problems only (the [M, M] output per particle is 3.2 MB for Panda)
+    Bc = min(B, 16)
+    shc = ops.make_shape(Bc, G, K, S, T, n, torch.float32)
+    xc, mc, wc = xs[:Bc].contiguous(), means[:Bc].contiguous(), torch.softmax(-costs[:Bc] / float(w["temperature"]) * 1e-3, dim=-1).contiguous()
+    covb = torch.empty(Bc, NP, M, M, device=dev)
+    bf16_tf = (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1663.8) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1663.8)
+    for tc, nm in ((1, "weighted covariance (tcgen05 kind::tf32, 3xTF32)"), (0, "weighted covariance (CUDA cores, fp64 accumulate)")):
+        def kcov(tc=tc):
+            ops._lib.check(ops._lib.load().sgpmp_weighted_cov(ops.C.byref(shc), ops._ptr(xc), ops._ptr(mc), ops._ptr(wc), ops._ptr(covb), tc, ops._stream()), "cov")
+        ms = timeit(kcov)
+        fl = 2.0 * Bc * NP * M * M * S
+        tiles = (M + 127) // 128
+        issued = 3 * 2.0 * Bc * NP * (tiles * (tiles + 1) // 2) * 128 * 128 * (-(-S // 32) * 32) if tc else fl   # upper-triangle tiles, 3xTF32
+        by = Bc * NP * (M * S + M * M + S) * 4
+        print(json.dumps({"kernel": nm, "workload": w["name"], "problems": Bc, "particles": Bc * NP, "M": M, "S": S, "ms": ms,
+                          "useful_tflops": fl / (ms * 1e-3) / 1e12, "issued_tflops": issued / (ms * 1e-3) / 1e12,
+                          "tf32_peak_tflops_est": bf16_tf / 2, "frac_of_tf32_peak_issued": (issued / (ms * 1e-3) / 1e12) / (bf16_tf / 2) if tc else None,
+                          "algorithmic_bytes": by, "achieved_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm": by / (ms * 1e-3) / 1e9 / hbm,
+                          "note": "diagnostic without reference counterpart; tf32 peak estimated as half the measured bf16 GEMM peak"}), flush=True)
+
     # K1: latency
     from stoch_gpmp_b200.planner import prior_blocks
     for TT in (64, 1024):

@@ -8,16 +8,16 @@
 // layout [M][S] is exactly the K-major operand layout the tensor core wants for both A and B.
 //
 // fp32 kernel (sm_100a):
-//   * one CTA (128 threads) per 128 x 128 tile of C and particle; K = S is consumed in chunks of 32 samples;
-//   * per chunk every thread prepares ONE row of the A block and one of the B block: subtract the mean, scale by sqrt(w_s),
-//     split into a TF32 head and a TF32 tail (3xTF32: hi*hi + hi*lo + lo*hi keeps ~2^-21 relative accuracy, plain TF32 would
+//   * one CTA (256 threads) per 128 x 128 tile of the upper triangle of C and particle; K = S is consumed in chunks of 32 samples;
+//   * per chunk the 256 threads stage the A and B blocks with coalesced 128-byte row segments (8 lanes per row, one 16-byte
+//     core-matrix row per lane): subtract the mean, scale by sqrt(w_s), split into a TF32 head and a TF32 tail (3xTF32: hi*hi + hi*lo + lo*hi keeps ~2^-21 relative accuracy, plain TF32 would
 //     give 2^-11) and stores them in the canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes per core matrix);
 //   * fence.proxy.async + __syncthreads, then ONE thread issues 4 (k steps of 8) x 3 tcgen05.mma.kind::tf32 with shared-memory
 //     descriptors for A and B, accumulating into 128 lanes x 128 columns of TMEM, and commits them to an mbarrier;
-//   * everybody waits on the mbarrier (the shared-memory chunk may then be overwritten);
-//   * epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld.32x32b.x32 and writes rows of C.
-// The operation is tiny (2 M^2 S = 0.8 GFLOP per Panda particle), so the kernel favours a simple, serial load -> MMA
-// chunk loop over a TMA/mbarrier pipeline.
+//   * two shared-memory stages: chunk c+1 is staged while the MMAs of chunk c run; a stage is reused after waiting on its mbarrier;
+//   * epilogue: each warp reads its 32 TMEM lanes (two 32-column blocks per warp) with tcgen05.ld.32x32b.x32 and writes rows of C.
+// The operation is tiny (2 M^2 S = 0.8 GFLOP per Panda particle) and its operands need arithmetic before they reach the tensor
+// core (mean subtraction, weighting, TF32 split), so the staging is done by the CTA's threads rather than by TMA.
 // fp64: CUDA-core kernel, one thread per entry (fp64 planners are parity configurations).
 #include "sgpmp_common.cuh"
 
@@ -25,9 +25,14 @@ namespace sgpmp {
 
 constexpr int COV_TILE = 128;     // rows of the A block = rows of the B block = UMMA M = UMMA N
 constexpr int COV_KC = 32;        // samples per chunk (4 UMMA K steps of 8 tf32)
-constexpr uint32_t COV_LBO = 128;                    // bytes between core matrices adjacent in K
-constexpr uint32_t COV_SBO = (COV_KC / 4) * 128;     // bytes between 8-row groups: all K core matrices of a group are contiguous
-constexpr int COV_OP_BYTES = COV_TILE * COV_KC * 4;  // one operand buffer (16 KiB)
+// A core matrix is 8 rows x 16 bytes, contiguous (128 B).  K-adjacent core matrices are placed 144 B apart (16 B of padding):
+// the 8 lanes that stage one row write 16-byte pieces 144 B apart = 8 different bank groups (128 B apart they would all
+// hit the same four banks, an 8-way conflict on every STS.128).
+constexpr uint32_t COV_LBO = 144;                    // bytes between core matrices adjacent in K
+constexpr uint32_t COV_SBO = (COV_KC / 4) * COV_LBO; // bytes between 8-row groups: all K core matrices of a group are contiguous
+constexpr int COV_OP_BYTES = (COV_TILE / 8) * COV_SBO;   // one operand buffer (18 KiB)
+constexpr int COV_THREADS = 256;                     // 8 warps stage; one thread issues the MMAs; all 8 warps drain TMEM
+constexpr int COV_STAGES = 2;                        // shared-memory stages: chunk c+1 is staged while the MMAs of chunk c run
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,19 +64,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         "DONE:\n\t}\n" ::"r"(mbar), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(COV_THREADS, 1)
 weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ samples, const float* __restrict__ means,
                        const float* __restrict__ weights, float* __restrict__ cov) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* a_hi = smem_raw;
-    unsigned char* a_lo = a_hi + COV_OP_BYTES;
-    unsigned char* b_hi = a_lo + COV_OP_BYTES;
-    unsigned char* b_lo = b_hi + COV_OP_BYTES;
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar[COV_STAGES];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int bp = blockIdx.y, ti = blockIdx.x / tiles, tj = blockIdx.x - ti * tiles;
+    // C is symmetric: only the tiles with tj >= ti are computed (tiles (tiles + 1) / 2 CTAs per particle); off-diagonal tiles
+    // are stored twice (as computed and transposed)
+    const int bp = blockIdx.y;
+    int ti = 0, tj = (int)blockIdx.x;
+    while (tj >= tiles - ti) { tj -= tiles - ti; ++ti; }
+    tj += ti;
     const int i0 = ti * COV_TILE, j0 = tj * COV_TILE;
     const float* xs = samples + (size_t)bp * M * S;
     const float* mu = means + (size_t)bp * M;
@@ -83,7 +89,8 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1) : "memory");
+        for (int k = 0; k < COV_STAGES; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[k])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -91,38 +98,73 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = tmem_base_s;
 
-    // this thread's operand rows: row tid of the A block (state component i0 + tid) and of the B block (j0 + tid)
-    const int ia = i0 + tid, jb = j0 + tid;
-    const float mua = ia < M ? mu[ia] : 0.f, mub = jb < M ? mu[jb] : 0.f;
-    const uint32_t row_off = (uint32_t)(tid >> 3) * COV_SBO + (uint32_t)(tid & 7) * 16;   // core-matrix row of this thread
+    // Staging map: thread = (row group rg = tid / 8, K block kb = tid % 8).  In pass it the thread handles row
+    // RPP it + rg of the block (RPP = COV_THREADS / 8 rows per pass) and its samples [s0 + 4 kb, s0 + 4 kb + 4): the 8 lanes of a row read one contiguous 128-byte line
+    // (coalesced, every line touched exactly once), and what a thread holds is exactly one 16-byte core-matrix row.
+    const int rg = tid >> 3, kb = tid & 7;
     const bool same = (ti == tj);
-    uint32_t phase = 0;
+    const bool vec = (S & 3) == 0;
     const int n_chunks = (S + COV_KC - 1) / COV_KC;
     for (int c = 0; c < n_chunks; ++c) {
-        const int s0 = c * COV_KC;
+        // stage buffers of this chunk; they are free once the MMAs of chunk c - COV_STAGES have completed (k-th arrival on the
+        // stage's mbarrier completes its phase k)
+        const int stg = c % COV_STAGES;
+        unsigned char* a_hi = smem_raw + (size_t)stg * 4 * COV_OP_BYTES;
+        unsigned char* a_lo = a_hi + COV_OP_BYTES;
+        unsigned char* b_hi = a_lo + COV_OP_BYTES;
+        unsigned char* b_lo = b_hi + COV_OP_BYTES;
+        const int s0 = c * COV_KC + 4 * kb;
+        float sw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sw[q] = (s0 + q < S) ? sqrtf(w[s0 + q]) : 0.f;
         // ---- stage Y = sqrt(w) (x - mu) for this chunk, split into TF32 head and tail ---------------------------------
+        // all 16 row segments of this thread are requested before any is consumed: one HBM/L2 round trip per chunk
+        constexpr int RPP = COV_THREADS / 8, NIT = COV_TILE / RPP;
+        float4 v[2][NIT];
+        float m[2][NIT];
 #pragma unroll
-        for (int kb = 0; kb < COV_KC / 4; ++kb) {         // one 16-byte core-matrix row (4 samples) at a time
-            float ah[4], al[4], bh[4], bl[4];
+        for (int op = 0; op < 2; ++op) {
+            if (op == 1 && same) break;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int s = s0 + 4 * kb + q;
-                const float sw = s < S ? sqrtf(w[s]) : 0.f;
-                const float ya = (ia < M && s < S) ? sw * (xs[(size_t)ia * S + s] - mua) : 0.f;
-                ah[q] = to_tf32(ya);
-                al[q] = to_tf32(ya - ah[q]);
-                if (!same) {
-                    const float yb = (jb < M && s < S) ? sw * (xs[(size_t)jb * S + s] - mub) : 0.f;
-                    bh[q] = to_tf32(yb);
-                    bl[q] = to_tf32(yb - bh[q]);
+            for (int it = 0; it < NIT; ++it) {
+                const int row = (op ? j0 : i0) + RPP * it + rg;
+                v[op][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                m[op][it] = 0.f;
+                if (row < M) {
+                    m[op][it] = mu[row];
+                    const float* src = xs + (size_t)row * S + s0;
+                    if (vec) {
+                        if (s0 < S) v[op][it] = *reinterpret_cast<const float4*>(src);
+                    } else {
+                        if (s0 + 0 < S) v[op][it].x = src[0];
+                        if (s0 + 1 < S) v[op][it].y = src[1];
+                        if (s0 + 2 < S) v[op][it].z = src[2];
+                        if (s0 + 3 < S) v[op][it].w = src[3];
+                    }
                 }
             }
-            const uint32_t off = row_off + (uint32_t)kb * COV_LBO;
-            *reinterpret_cast<float4*>(a_hi + off) = make_float4(ah[0], ah[1], ah[2], ah[3]);
-            *reinterpret_cast<float4*>(a_lo + off) = make_float4(al[0], al[1], al[2], al[3]);
-            if (!same) {
-                *reinterpret_cast<float4*>(b_hi + off) = make_float4(bh[0], bh[1], bh[2], bh[3]);
-                *reinterpret_cast<float4*>(b_lo + off) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+        }
+        if (c >= COV_STAGES) {      // (the global loads above are already in flight)
+            mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((c / COV_STAGES) - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+            if (op == 1 && same) break;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int r = RPP * it + rg;
+                const uint32_t off = (uint32_t)(r >> 3) * COV_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kb * COV_LBO;
+                const float x4[4] = {v[op][it].x, v[op][it].y, v[op][it].z, v[op][it].w};
+                float hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float y = sw[q] * (x4[q] - m[op][it]);       // rows >= M hold x = m = 0, samples >= S have sw = 0
+                    hi[q] = to_tf32(y);
+                    lo[q] = to_tf32(y - hi[q]);
+                }
+                *reinterpret_cast<float4*>((op ? b_hi : a_hi) + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>((op ? b_lo : a_lo) + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
@@ -149,18 +191,21 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
                              ::"r"(tmem_acc), "l"(dal), "l"(dbh), "r"(COV_IDESC), "r"(1u) : "memory");
             }
             // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
         }
-        mbar_wait(smem_u32(&mbar), phase);
-        phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // ---- epilogue: TMEM -> registers -> C.  Warp w owns TMEM lanes [32 w, 32 w + 32) = rows i0 + 32 w + lane -----------
-    const int row = i0 + tid;
+    // the last commit covers every MMA issued before it
+    mbar_wait(smem_u32(&mbar[(n_chunks - 1) % COV_STAGES]), (uint32_t)(((n_chunks - 1) / COV_STAGES) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: TMEM -> registers -> C.  A warp may read the TMEM lanes [32 (w % 4), 32 (w % 4) + 32) = rows i0 + 32 (w % 4) +
+    // lane; warps 0-3 take the column blocks 0 and 1, warps 4-7 the blocks 2 and 3 ---------------------------------------------
+    const int lane_grp = warp & 3;
+    const int row = i0 + lane_grp * 32 + (tid & 31);
+    constexpr int CB_PER_WARP = (COV_TILE / 32) / (COV_THREADS / 128);
 #pragma unroll 1
-    for (int cb = 0; cb < COV_TILE / 32; ++cb) {
+    for (int cb = (warp >> 2) * CB_PER_WARP; cb < (warp >> 2) * CB_PER_WARP + CB_PER_WARP; ++cb) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cb * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -172,10 +217,21 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < M) {
+            const int c0 = j0 + cb * 32;
+            if ((M & 3) == 0 && c0 + 32 <= M) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int col = j0 + cb * 32 + q;
-                if (col < M) C[(size_t)row * M + col] = __uint_as_float(r[q]);
+                for (int q = 0; q < 32; q += 4)
+                    *reinterpret_cast<float4*>(C + (size_t)row * M + c0 + q) =
+                        make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (c0 + q < M) C[(size_t)row * M + c0 + q] = __uint_as_float(r[q]);
+            }
+            if (!same) {            // transposed copy: consecutive lanes write consecutive addresses
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (c0 + q < M) C[(size_t)(c0 + q) * M + row] = __uint_as_float(r[q]);
             }
         }
     }
@@ -213,9 +269,9 @@ extern "C" int sgpmp_weighted_cov(const sgpmp_shape_t* shape, const void* sample
     cudaStream_t st = (cudaStream_t)stream;
     if (shape->dtype == SGPMP_F32 && use_tensor_cores) {
         const int tiles = (M + COV_TILE - 1) / COV_TILE;
-        const size_t smem = 4 * (size_t)COV_OP_BYTES + 1024;
+        const size_t smem = (size_t)COV_STAGES * 4 * COV_OP_BYTES + 1024;
         cudaFuncSetAttribute(weighted_cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        weighted_cov_tc_kernel<<<dim3((unsigned)(tiles * tiles), (unsigned)BP), 128, smem, st>>>(
+        weighted_cov_tc_kernel<<<dim3((unsigned)(tiles * (tiles + 1) / 2), (unsigned)BP), COV_THREADS, smem, st>>>(
             M, S, tiles, (const float*)samples, (const float*)means, (const float*)weights, (float*)cov);
         SGPMP_CHECK_LAUNCH("sgpmp_weighted_cov");
         return SGPMP_OK;
