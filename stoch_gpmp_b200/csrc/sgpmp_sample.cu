@@ -140,7 +140,12 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
 template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
                          uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st) {
-    if (!eps_in) {      // in-kernel RNG: thread-per-sample kernel for the instantiated DoF counts
+    // In-kernel RNG: thread-per-sample kernel for the instantiated DoF counts — when there are enough samples to fill the
+    // machine with one thread each.  Few samples with long horizons (C5: one problem, T up to 1024) are latency-bound on the
+    // sequential recurrence, so they take the thread-per-(sample, DoF) kernel below: n times the threads, the same stream
+    // (T = 1024, n = 7, fp64, 2,048 samples: 2.69 ms -> see profiles/r1/c5_sweep.jsonl).
+    const long n_samples_total = (long)sh.B * sh.G * sh.K * sh.S;
+    if (!eps_in && n_samples_total >= 148L * 512) {
         int rc = SGPMP_ERR_UNSUPPORTED;
         switch (sh.n_dof) {
 #define SGPMP_DOF_CASE(N) case N: rc = launch_sample_rng<real, N>(sh, tables, means, seed, draw, samples, eps_out, st); break;
