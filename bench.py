@@ -14,7 +14,9 @@ workload N=1: BASELINE.json configs[3], "Panda 7-DoF batched: 4096 problems x 4 
 value    inputs resident in HBM, fused kernel only (CUDA events around each step, L2 flushed between steps).
 e2e      same metric through the public API (StochGPMPBatch.optimize) from HOST buffers: per step the
          observation (obstacle spheres) is copied H2D from pinned memory and the plan (particle means) is
-         read back D2H, both inside the timed region.
+         read back D2H, both inside the timed region (host clock).  The batch is sharded into --e2e-shards
+         StochGPMPBatch objects on their own streams so that a shard's D2H overlaps the next shard's kernel;
+         the host waits for every shard at the end of every step.
 The reference arm (--impl reference) times the reference's CPU algorithm (oracle/reference_port.py, pinned to
 the real reference by tests/test_reference_port.py; the reference itself is pure Python and does not travel
 to the GPU box) on the host cores, on a bounded sample of the same workload.
@@ -265,34 +267,54 @@ def run_ours(args, rank, world, local_rank):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # ---------------- timed: end to end from host buffers ("e2e")
-    means_host = torch.empty(pl.particle_means.shape, dtype=torch.float32).pin_memory()
-    h2d = sph_host.numel() * 4 if sph_host is not None else 0
-    if sph_host is None:       # planar: the per-step host input is the start/goal set of every problem
-        sg_host = torch.tensor(np.concatenate([wl["start"].reshape(B, -1), wl["goals"].reshape(B, -1)], 1), dtype=torch.float32).pin_memory()
-        sg_dev = torch.empty_like(sg_host, device=dev)
-        h2d = sg_host.numel() * 4
-    d2h = means_host.numel() * 4
-    for _ in range(2):
-        if sph_host is not None:
-            sph_dev.copy_(sph_host, non_blocking=True)
-        pl.optimize(return_samples=False, **obs)
-        means_host.copy_(pl.particle_means, non_blocking=True)
+    # Public API only: the batch is sharded into E2E_SHARDS StochGPMPBatch objects (problem_offset keeps every RNG stream where it
+    # was, results are bit-identical to the single batch: tests/test_gpu_planner.py::test_fused_problem_sharding_invariance), one
+    # CUDA stream each.  Per step every shard copies its inputs H2D, runs optimize() and copies its plan D2H on its own stream, so
+    # the 58.7 MB D2H of shard k rides under the kernel of shard k+1; the host waits for ALL shards before the next step starts
+    # ("the user has the plan on the host every step").
+    n_sh = max(1, min(args.e2e_shards, B))
+    while B % n_sh:
+        n_sh -= 1
+    Bs = B // n_sh
+    shards = []
+    for k in range(n_sh):
+        a = k * Bs
+        wk = dict(w, start=wl["start"][a:a + Bs], goals=wl["goals"][a:a + Bs], spheres=None if wl["spheres"] is None else wl["spheres"][a:a + Bs])
+        plk = build_planner(wk, Bs, dev, problem_offset=lo + a, seed=0) if n_sh > 1 else pl
+        sk = dict(pl=plk, stream=torch.cuda.Stream(device=dev), means_host=torch.empty(plk.particle_means.shape, dtype=torch.float32).pin_memory())
+        if wl["spheres"] is not None:
+            sk["in_host"] = torch.tensor(wk["spheres"], dtype=torch.float32).pin_memory()
+            sk["in_dev"] = sk["in_host"].to(dev)
+            sk["obs"] = {"obstacle_spheres": sk["in_dev"]}
+        else:      # planar: the per-step host input is the start/goal set of every problem
+            sk["in_host"] = torch.tensor(np.concatenate([wk["start"].reshape(Bs, -1), wk["goals"].reshape(Bs, -1)], 1), dtype=torch.float32).pin_memory()
+            sk["in_dev"] = torch.empty_like(sk["in_host"], device=dev)
+            sk["obs"] = {}
+        shards.append(sk)
+    h2d = sum(sk["in_host"].numel() for sk in shards) * 4
+    d2h = sum(sk["means_host"].numel() for sk in shards) * 4
+
+    def e2e_step():
+        for sk in shards:
+            with torch.cuda.stream(sk["stream"]):
+                sk["in_dev"].copy_(sk["in_host"], non_blocking=True)
+                sk["pl"].optimize(return_samples=False, **sk["obs"])
+                sk["means_host"].copy_(sk["pl"].particle_means, non_blocking=True)
+        for sk in shards:
+            sk["stream"].synchronize()                      # the user has the whole plan on the host every step
+
+    torch.cuda.synchronize()
+    for _ in range(3):
+        e2e_step()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_e2e0 = _lib.launch_count()
     e2e_wall0 = time.perf_counter()
-    e0.record()
     for _ in range(args.steps):
-        if sph_host is not None:
-            sph_dev.copy_(sph_host, non_blocking=True)
-        else:
-            sg_dev.copy_(sg_host, non_blocking=True)
-        pl.optimize(return_samples=False, **obs)
-        means_host.copy_(pl.particle_means, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the user has the plan on the host every step
-    e1.record()
+        e2e_step()
+    e2e_wall = time.perf_counter() - e2e_wall0               # host clock: every step ends with a host-side wait on all streams
+    launches_e2e = _lib.launch_count() - launches_e2e0
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_wall = time.perf_counter() - e2e_wall0
+    e2e_ms = e2e_wall * 1e3
 
     # ---------------- max over ranks
     t = torch.tensor([dev_ms, e2e_ms, wall * 1e3, e2e_wall * 1e3], dtype=torch.float64, device=dev)
@@ -371,7 +393,9 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "256 MiB write between timed steps (outside the CUDA-event pair)", "prior": "fp64 factor, fp32 run-time",
                        "rng": "in-kernel Philox4x32-10"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                                   "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
+                                   "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "shards_per_gpu": n_sh,
+                                   "launches_per_step": launches_e2e / args.steps,
+                                   "note": "StochGPMPBatch per shard on its own stream: H2D inputs, optimize(), D2H plan; host waits for all shards every step"},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "ms_per_plan": {"iterations": plan_iters, "single_problem_ms": plan_ms_single,
                             "amortised_over_batch_ms": ms_per_step * plan_iters / B,
@@ -388,6 +412,7 @@ def main():
     ap.add_argument("--workload", default="panda", choices=["panda", "planar"])
     ap.add_argument("--problems-per-gpu", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-shards", type=int, default=8, help="StochGPMPBatch shards (CUDA streams) per GPU in the end-to-end measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
