@@ -276,32 +276,23 @@ def run_ours(args, rank, world, local_rank):
     while B % n_sh:
         n_sh -= 1
     Bs = B // n_sh
-    shards = []
+    from stoch_gpmp_b200.parallel import StreamShards
+    planners, host_in = [], []
     for k in range(n_sh):
         a = k * Bs
         wk = dict(w, start=wl["start"][a:a + Bs], goals=wl["goals"][a:a + Bs], spheres=None if wl["spheres"] is None else wl["spheres"][a:a + Bs])
-        plk = build_planner(wk, Bs, dev, problem_offset=lo + a, seed=0) if n_sh > 1 else pl
-        sk = dict(pl=plk, stream=torch.cuda.Stream(device=dev), means_host=torch.empty(plk.particle_means.shape, dtype=torch.float32).pin_memory())
+        planners.append(build_planner(wk, Bs, dev, problem_offset=lo + a, seed=0) if n_sh > 1 else pl)
         if wl["spheres"] is not None:
-            sk["in_host"] = torch.tensor(wk["spheres"], dtype=torch.float32).pin_memory()
-            sk["in_dev"] = sk["in_host"].to(dev)
-            sk["obs"] = {"obstacle_spheres": sk["in_dev"]}
+            host_in.append(torch.tensor(wk["spheres"], dtype=torch.float32).pin_memory())
         else:      # planar: the per-step host input is the start/goal set of every problem
-            sk["in_host"] = torch.tensor(np.concatenate([wk["start"].reshape(Bs, -1), wk["goals"].reshape(Bs, -1)], 1), dtype=torch.float32).pin_memory()
-            sk["in_dev"] = torch.empty_like(sk["in_host"], device=dev)
-            sk["obs"] = {}
-        shards.append(sk)
-    h2d = sum(sk["in_host"].numel() for sk in shards) * 4
-    d2h = sum(sk["means_host"].numel() for sk in shards) * 4
+            host_in.append(torch.tensor(np.concatenate([wk["start"].reshape(Bs, -1), wk["goals"].reshape(Bs, -1)], 1), dtype=torch.float32).pin_memory())
+    shards = StreamShards(planners, obs_key="obstacle_spheres" if wl["spheres"] is not None else None, host_inputs=host_in)
+    h2d = sum(h.numel() for h in host_in) * 4
+    d2h = sum(m.numel() for m in shards.host_means) * 4
 
     def e2e_step():
-        for sk in shards:
-            with torch.cuda.stream(sk["stream"]):
-                sk["in_dev"].copy_(sk["in_host"], non_blocking=True)
-                sk["pl"].optimize(return_samples=False, **sk["obs"])
-                sk["means_host"].copy_(sk["pl"].particle_means, non_blocking=True)
-        for sk in shards:
-            sk["stream"].synchronize()                      # the user has the whole plan on the host every step
+        shards.step()
+        shards.wait()                                       # the user has the whole plan on the host every step
 
     torch.cuda.synchronize()
     for _ in range(3):

@@ -38,3 +38,45 @@ def allreduce_stats(stats, group=None):
     bufs = [torch.empty_like(stats) for _ in range(world)]
     dist.all_gather(bufs, stats.contiguous(), group=group)
     return merge_stats(bufs)
+
+
+class StreamShards:
+    """Host-to-host pipelining on ONE GPU: the shards of a problem batch (one StochGPMPBatch each, built by the caller with
+    `problem_offset` = start of the shard, so every result is bit-identical to the unsharded batch) run on their own CUDA
+    streams.  `step()` copies every shard's observation H2D from pinned memory, runs optimize() and copies the shard's plan
+    (particle means) D2H; the D2H of shard k overlaps the kernel of shard k+1.  `wait()` blocks the host until every plan is in
+    its pinned buffer.
+
+        shards = StreamShards([planner_0, ..., planner_7], obs_key='obstacle_spheres', host_inputs=[pinned_0, ...])
+        shards.step(); shards.wait(); shards.host_means[k]    # [B_k, NP, T, d] pinned
+    """
+
+    def __init__(self, planners, obs_key=None, host_inputs=None):
+        self.planners = list(planners)
+        dev = self.planners[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.planners]
+        ready = torch.cuda.current_stream(dev).record_event()      # the planners were built (reset()) on the current stream
+        for st in self.streams:
+            st.wait_event(ready)
+        self.host_means = [torch.empty(p.particle_means.shape, dtype=p.dtype).pin_memory() for p in self.planners]
+        self.obs_key = obs_key
+        self.host_inputs = None
+        self.dev_inputs = None
+        if host_inputs is not None:
+            self.host_inputs = [h if h.is_pinned() else h.pin_memory() for h in host_inputs]
+            self.dev_inputs = [torch.empty_like(h, device=dev) for h in self.host_inputs]
+
+    def step(self, **optimize_kwargs):
+        for k, (p, st) in enumerate(zip(self.planners, self.streams)):
+            with torch.cuda.stream(st):
+                obs = {}
+                if self.host_inputs is not None:
+                    self.dev_inputs[k].copy_(self.host_inputs[k], non_blocking=True)
+                    if self.obs_key is not None:
+                        obs[self.obs_key] = self.dev_inputs[k]
+                p.optimize(return_samples=False, **obs, **optimize_kwargs)
+                self.host_means[k].copy_(p.particle_means, non_blocking=True)
+
+    def wait(self):
+        for st in self.streams:
+            st.synchronize()

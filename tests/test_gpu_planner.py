@@ -298,3 +298,28 @@ def test_user_supplied_initial_means(cuda):
     assert rel(pl.particle_means.cpu().numpy(), g['it0_means_post']) < 1e-10
     with pytest.raises(AssertionError):
         pl.reset(initial_particle_means=torch.zeros(G, K + 1, T, d, device=cuda, dtype=torch.float64))
+
+
+def test_stream_shards_equal_single_batch(cuda):
+    """parallel.StreamShards (shards of a batch on their own streams, plans copied to pinned host memory) == the unsharded
+    batch, bit for bit (RNG streams are keyed by global problem ids)."""
+    import bench
+    from stoch_gpmp_b200.parallel import StreamShards
+    B, n_sh = 8, 4
+    w = bench.workload('panda', B)
+    w = dict(w, S=64, T=16)
+    whole = bench.build_planner(w, B, cuda)
+    sph = torch.tensor(w['spheres'], dtype=torch.float32, device=cuda)
+    whole.optimize(opt_iters=2, return_samples=False, obstacle_spheres=sph)
+    Bs = B // n_sh
+    planners, host_in = [], []
+    for k in range(n_sh):
+        a = k * Bs
+        wk = dict(w, start=w['start'][a:a + Bs], goals=w['goals'][a:a + Bs], spheres=w['spheres'][a:a + Bs])
+        planners.append(bench.build_planner(wk, Bs, cuda, problem_offset=a))
+        host_in.append(torch.tensor(wk['spheres'], dtype=torch.float32))
+    sh = StreamShards(planners, obs_key='obstacle_spheres', host_inputs=host_in)
+    sh.step(opt_iters=2)
+    sh.wait()
+    got = torch.cat(sh.host_means, 0)
+    assert torch.equal(got, whole.particle_means.cpu())
