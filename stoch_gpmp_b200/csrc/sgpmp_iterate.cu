@@ -30,6 +30,9 @@
 #ifndef SGPMP_MINB256
 #define SGPMP_MINB256 3
 #endif
+#ifndef SGPMP_MINB128_SMALL
+#define SGPMP_MINB128_SMALL 10    // n_dof <= 3 (planar): the whole state is 4-6 registers; 51 registers per thread, 10 CTAs per SM (8: 1.79 ms, 10: 1.77, 12: 1.81)
+#endif
 #ifndef SGPMP_MINB_PACKED
 #define SGPMP_MINB_PACKED 2
 #endif
@@ -71,7 +74,7 @@ template <> struct PackV<float, 1> { using type = F2; };
 // shared memory (cluster.map_shared_rank) with four cluster barriers per iteration, then every CTA applies the
 // identical update to its own copy of mu.  No global memory or extra launch is involved.
 template <typename real, int PACK, int N, int BS, int CHAIN, int CL>
-__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (PACK == 1 ? SGPMP_MINB_PACKED : (BS == 256 ? SGPMP_MINB256 : SGPMP_MINB128)) : 1))
+__global__ void __launch_bounds__(BS, (sizeof(real) == 4 ? (PACK == 1 ? SGPMP_MINB_PACKED : (BS == 256 ? SGPMP_MINB256 : ((N <= 3 && CL == 1 && BS == 128) ? SGPMP_MINB128_SMALL : SGPMP_MINB128))) : 1))
 iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant__ IterArgs<real> A) {
     using V = typename PackV<real, PACK>::type;
     constexpr int W = VT<V>::W;
@@ -470,7 +473,12 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
         // dof-pair packing covers the occupancy-map field and the Panda structure; generic FK chains stay scalar
         const bool pairs_ok = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (pack == 2 && pairs_ok) {
-            if (sh.S > 128 && !bs128) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
+            // CTA size: 256 threads for the FK-heavy chains (Panda: 17.6 ms against 19.0 ms with 128 at C4); without link fields
+            // (planar: a short per-sample body, so the per-iteration block phases — b = P mu, softmax, update — weigh more)
+            // 128-thread CTAs overlap those phases across more resident CTAs: 2.23 -> 1.96 ms at 4096 x 4 x 256.
+            static const bool bs256_forced = force_bs && atoi(force_bs) == 256;
+            const bool light = (CHAIN == 0) && !(P.has_spheres || P.has_self);
+            if (sh.S > 128 && !bs128 && (!light || bs256_forced)) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
             return launch_iterate_nb<real, 2, N, 128, CHAIN>(sh, P, A, st);
         }
 #ifdef SGPMP_ENABLE_TWO_SAMPLE_PACKING   // measured 4 % slower than dof pairs (register pressure); kept for experiments
