@@ -336,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
     flops, mufu = algorithmic_flops_per_traj(w)
     ach_tf = ntraj_rank * flops / (ms_per_step * 1e-3) / 1e12
     ach_mufu = ntraj_rank * mufu / (ms_per_step * 1e-3) / 1e12
-    roof = {"bound": "fp32", "kernel": "sgpmp::iterate_kernel<float,2,%d,256,%d>" % (w["n_dof"], 1 if w["spheres"] is not None else 0), "achieved": ach_tf,
+    roof = {"bound": "fp32", "kernel": "sgpmp::iterate_kernel<float,2,%d,%d,%d,1>" % (w["n_dof"], 128 if (w["spheres"] is None and B * w["G"] * w["K"] >= 10 * 148) else 256, 1 if w["spheres"] is not None else 0), "achieved": ach_tf,
             "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["fp32_tflops"], "traffic": traffic,
             "traffic_source": "profiles/r1/traffic.json (ncu --set full capture of this command)" if traffic else None,
             "ncu": ncu_facts,

@@ -79,7 +79,7 @@ typedef struct sgpmp_shape {
 } sgpmp_shape_t;
 
 /* Lowered form of the reference's cost objects (what StochGPMP.__init__ extracts from cost.cost_list):
- *   CostGP          cost_functions.py:90-146   sigma_start, sigma_gp, start_state, dt
+ *   CostGP          cost_functions.py:90-146   sigma_start, sigma_gp, start_state, dt   (CostGPTrajectory :171-218: no start factor)
  *   CostGoalPrior   cost_functions.py:342-388  sigma_goal_prior, multi_goal_states
  *   CostCollision   cost_functions.py:223-261  sigma_coll + field:
  *       ObstacleMap         envs/obst_map.py:108-188     (occupancy grid lookup)
@@ -92,7 +92,7 @@ typedef struct sgpmp_shape {
  * restated as a serial chain of fixed transforms + revolute z joints. */
 typedef struct sgpmp_cost_desc {
     double dt;
-    double sigma_start;
+    double sigma_start;       /* <= 0: no start factor (CostGPTrajectory, cost_functions.py:171-218) */
     double sigma_gp;
     double sigma_goal_prior;  /* <= 0: no CostGoalPrior term */
     double temperature;       /* weight of the IS term; 0 disables it */

@@ -34,7 +34,7 @@ def _np(t):
 def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_sigmas, cost_sigmas,
              temperature, step_size, iters, map_params=None, spheres=None, initial_particle_means=None,
              sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None, field_type='rbf', clamp_sdf=False,
-             interp=None, self_interp=None, ee_goal=None):
+             interp=None, self_interp=None, ee_goal=None, gp_trajectory=False):
     ref = ref_loader.load()
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
     start_state = torch.tensor(start, **ta)
@@ -50,7 +50,11 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
     for k, v in cost_sigmas.items():
         rec['cost_' + k] = v
 
-    cost_list = [ref.CostGP(n_dof, T, start_state, dt, cost_sigmas, ta)]
+    if gp_trajectory:        # CostGPTrajectory (cost_functions.py:171-218): GP transition factors without the start factor
+        rec['cost_sigma_start'] = -1.0
+        cost_list = [ref.CostGPTrajectory(n_dof, T, start_state, dt, cost_sigmas, ta)]
+    else:
+        cost_list = [ref.CostGP(n_dof, T, start_state, dt, cost_sigmas, ta)]
     term_names = ['gp']
     if goals is not None and sigma_goal_prior is not None:
         cost_list.append(ref.CostGoalPrior(n_dof, T, multi_goal_states=goal_states, num_particles_per_goal=K,
@@ -173,7 +177,7 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
                 val = c(trajs, x_trajs=x_trajs, **obs)
                 tot = tot + val
                 rec[tag + pre + 'term_' + nm] = _np(val.reshape(NP, S))
-            if term_names[0] == 'gp':
+            if term_names[0] == 'gp' and not gp_trajectory:
                 # split CostGP into its start and transition parts with the reference's own factors
                 cgp = cost_list[0]
                 err_p = cgp.start_prior.get_error(trajs[:, [0]], calc_jacobian=False)
@@ -326,6 +330,13 @@ def main(only=None):
              temperature=200., step_size=0.5, iters=2, spheres=panda_spheres(5, 1))
 
 
+    # CostGPTrajectory in place of CostGP (no start factor), planar
+    run_case('planar_gptraj_f64', n_dof=2, T=12, dt=0.1, G=2, K=2, S=6, dtype=torch.float64, seed=13,
+             start=[0.3, -0.2, 0, 0], goals=[[1.0, 0.6, 0, 0], [-0.8, 0.9, 0, 0]],
+             planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.1,
+                                 sigma_start_sample=1.0, sigma_goal_sample=1.0, sigma_gp_sample=2.0),
+             cost_sigmas=dict(sigma_gp=2.), sigma_coll=0.5, sigma_goal_prior=1.0,
+             temperature=20., step_size=0.5, iters=1, map_params=SOFT_MAP, gp_trajectory=True)
     # the COMPLETE shipped Panda cost list [CostGP, CostGoalPrior, self, obstacle, CostGoal(EESE3DistanceField)]
     # (examples/panda_environment.py:66-90, sigma_goal = 0.00007), fp64 and fp32
     for nm, dt_ in (('panda_shipped_f64', torch.float64), ('panda_shipped_f32', torch.float32)):

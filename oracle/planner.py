@@ -33,7 +33,8 @@ def spec_from_golden(g):
     s = dict(n_dof=int(g['n_dof']), T=int(g['T']), dt=float(g['dt']), G=int(g['G']), K=int(g['K']), S=int(g['S']),
              temperature=float(g['temperature']), step_size=float(g['step_size']), start=g['start'],
              goals=g['goals'] if 'goals' in g.files else None,
-             cost_sigma_start=float(g['cost_sigma_start']), cost_sigma_gp=float(g['cost_sigma_gp']),
+             cost_sigma_start=float(g['cost_sigma_start']) if float(g['cost_sigma_start']) > 0 else None,      # None: CostGPTrajectory
+             cost_sigma_gp=float(g['cost_sigma_gp']),
              sigma_goal_prior=float(g['sigma_goal_prior']) if float(g['sigma_goal_prior']) > 0 else None,
              sigma_coll=float(g['sigma_coll']) if float(g['sigma_coll']) > 0 else None,
              dtype=str(g['dtype']))
@@ -98,7 +99,9 @@ def eval_costs(spec, samples, means, D, O, dtype=np.float64):
     lists, examples/panda_environment.py:90 — then the IS term)."""
     x = samples.astype(dtype)
     terms = {}
-    terms['start'] = C.cost_start(x, spec['start'].astype(dtype), spec['cost_sigma_start'])
+    # CostGPTrajectory (cost_functions.py:171-218) has no start factor
+    terms['start'] = (C.cost_start(x, spec['start'].astype(dtype), spec['cost_sigma_start']) if spec.get('cost_sigma_start') is not None
+                      else np.zeros(x.shape[:2], dtype=dtype))
     terms['gp'] = C.cost_gp(x, spec['dt'], spec['cost_sigma_gp'])
     total = terms['start'] + terms['gp']
     if spec.get('goals') is not None and spec.get('sigma_goal_prior') is not None:

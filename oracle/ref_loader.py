@@ -54,7 +54,7 @@ def load():
         sys.modules[tr].SE3_distance = se3_distance_torch
     ns = types.SimpleNamespace()
     from stoch_gpmp.planner import StochGPMP
-    from stoch_gpmp.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior, CostGoal
+    from stoch_gpmp.costs.cost_functions import CostCollision, CostComposite, CostGP, CostGoalPrior, CostGoal, CostGPTrajectory
     from stoch_gpmp.costs.fields import LinkDistanceField, LinkSelfDistanceField, EESE3DistanceField
     from stoch_gpmp.costs.factors.mp_priors_multi import MultiMPPrior
     from stoch_gpmp.envs.map_generator import generate_obstacle_map
@@ -63,6 +63,7 @@ def load():
     ns.CostCollision, ns.CostComposite, ns.CostGP, ns.CostGoalPrior = CostCollision, CostComposite, CostGP, CostGoalPrior
     ns.LinkDistanceField = LinkDistanceField
     ns.LinkSelfDistanceField, ns.EESE3DistanceField, ns.CostGoal = LinkSelfDistanceField, EESE3DistanceField, CostGoal
+    ns.CostGPTrajectory = CostGPTrajectory
     ns.MultiMPPrior = MultiMPPrior
     ns.generate_obstacle_map = generate_obstacle_map
     ns.ObstacleMap, ns.ObstacleRectangle, ns.ObstacleCircle = ObstacleMap, ObstacleRectangle, ObstacleCircle

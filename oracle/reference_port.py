@@ -82,7 +82,9 @@ class ReferencePort:
         _, self.Qinv_cost, self.Phi = dense_precision(2, spec['dt'], n, 1.0, spec['cost_sigma_gp'], None, dtype)
         self.start = torch.as_tensor(spec['start'], dtype=dtype)
         self.goals = None if spec.get('goals') is None else torch.as_tensor(spec['goals'], dtype=dtype)
-        self.K_start = torch.eye(self.d, dtype=dtype) / spec['cost_sigma_start'] ** 2
+        # cost_sigma_start None: CostGPTrajectory (cost_functions.py:171-218), no start factor
+        self.K_start = (torch.eye(self.d, dtype=dtype) / spec['cost_sigma_start'] ** 2 if spec.get('cost_sigma_start') is not None
+                        else torch.zeros(self.d, self.d, dtype=dtype))
         self.K_goal = None if spec.get('sigma_goal_prior') is None else torch.eye(self.d, dtype=dtype) / spec['sigma_goal_prior'] ** 2
         self.fk = fk
         self.map = torch.as_tensor(spec['map']).to(dtype) if 'map' in spec else None

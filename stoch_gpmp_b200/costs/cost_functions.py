@@ -97,8 +97,17 @@ class CostGoal(Cost):
 
 
 class CostGPTrajectory(Cost):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("CostGPTrajectory is outside the StochGPMP hot path (SURVEY §8a-4)")
+    """GP transition factors WITHOUT the start-state factor (cost_functions.py:171-218); `start_state` is stored but, as in the
+    reference, unused.  Lowered as a CostGP with no start term (sgpmp_cost_desc_t.sigma_start <= 0)."""
+    _term = 'gp+start'
+
+    def __init__(self, n_dof, traj_len, start_state, dt, sigma_params, tensor_args, **kwargs):
+        super().__init__(n_dof, traj_len)
+        self.start_state = start_state
+        self.dt = dt
+        self.sigma_start = None
+        self.sigma_gp = sigma_params['sigma_gp']
+        self.tensor_args = tensor_args
 
 
 class LoweredCost:
@@ -108,9 +117,9 @@ class LoweredCost:
         self.B, self.G, self.device, self.dtype = B, G, device, dtype
         gp = goal = coll = selfc = ee = None
         for c in composite.cost_list:
-            if isinstance(c, CostGP):
+            if isinstance(c, (CostGP, CostGPTrajectory)):
                 if gp is not None:
-                    raise NotImplementedError("more than one CostGP in cost_list")
+                    raise NotImplementedError("more than one CostGP / CostGPTrajectory in cost_list")
                 gp = c
             elif isinstance(c, CostGoalPrior):
                 if goal is not None:
@@ -139,11 +148,12 @@ class LoweredCost:
                 raise NotImplementedError("cost object %s cannot be lowered to the CUDA path (no CPU fallback)"
                                           % type(c).__name__)
         if gp is None:
-            raise NotImplementedError("cost_list needs a CostGP (start + GP factors)")
+            raise NotImplementedError("cost_list needs a CostGP (start + GP factors) or a CostGPTrajectory")
         n, d = composite.n_dof, 2 * composite.n_dof
         self.n_dof, self.T = n, composite.traj_len
         kw = dict(device=device, dtype=dtype)
-        self.dt, self.sigma_start, self.sigma_gp = float(gp.dt), float(gp.sigma_start), float(gp.sigma_gp)
+        self.dt, self.sigma_gp = float(gp.dt), float(gp.sigma_gp)
+        self.sigma_start = float(gp.sigma_start) if gp.sigma_start is not None else -1.0      # CostGPTrajectory: no start factor
         self.start = torch.as_tensor(gp.start_state).to(**kw).reshape(-1, d).expand(B, d).contiguous()
         self.goals, self.sigma_goal_prior = None, -1.0
         self.goal_K = self.goal_S = None

@@ -14,12 +14,13 @@ namespace sgpmp {
 template <typename real>
 int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostParams<real>& o) {
     memset(&o, 0, sizeof(o));
-    if (!(d.dt > 0) || !(d.sigma_start > 0) || !(d.sigma_gp > 0) || !d.start) {
-        set_error("cost desc: dt, sigma_start, sigma_gp must be > 0 and start non-null");
+    if (!(d.dt > 0) || !(d.sigma_gp > 0) || !d.start) {
+        set_error("cost desc: dt, sigma_gp must be > 0 and start non-null");
         return SGPMP_ERR_INVALID_ARG;
     }
     o.dt = (real)d.dt;
-    o.inv_sig_start2 = (real)(1.0 / (d.sigma_start * d.sigma_start));
+    // sigma_start <= 0: no start factor (CostGPTrajectory, cost_functions.py:171-218: the GP transition factors alone)
+    o.inv_sig_start2 = d.sigma_start > 0 ? (real)(1.0 / (d.sigma_start * d.sigma_start)) : (real)0;
     // Q^-1 blocks exactly as GPFactor.calc_Q_inv forms them (gp_factor.py:44-52)
     const double qc = 1.0 / (d.sigma_gp * d.sigma_gp);
     o.q11 = (real)(12.0 * pow(d.dt, -3.0) * qc);

@@ -25,7 +25,7 @@
 #include "sgpmp_rng.cuh"
 
 #ifndef SGPMP_MINB128
-#define SGPMP_MINB128 5
+#define SGPMP_MINB128 6       // 6 CTAs x 4 warps at 80 registers: the same 24 warps/SM as 3 x 256 threads, finer block phases
 #endif
 #ifndef SGPMP_MINB256
 #define SGPMP_MINB256 3
@@ -473,12 +473,15 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
         // dof-pair packing covers the occupancy-map field and the Panda structure; generic FK chains stay scalar
         const bool pairs_ok = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (pack == 2 && pairs_ok) {
-            // CTA size: 256 threads for the FK-heavy chains (Panda: 17.6 ms against 19.0 ms with 128 at C4); without link fields
-            // (planar: a short per-sample body, so the per-iteration block phases — b = P mu, softmax, update — weigh more)
-            // 128-thread CTAs overlap those phases across more resident CTAs: 2.23 -> 1.96 ms at 4096 x 4 x 256.
-            static const bool bs256_forced = force_bs && atoi(force_bs) == 256;
+            // CTA size.  Chains with link fields (Panda): 256 threads, 3 CTAs/SM.  (128 threads at 6 CTAs/SM — the same 24 warps
+            // per SM — measured 17.19 against 17.41 ms at 4096 problems, but 1.65 against 1.20 ms at 256 problems and 4.80 against
+            // 4.56 ms at 1024: each CTA then runs twice as long, so the last partial wave costs more than the finer block phases
+            // gain.  SGPMP_ITERATE_BS=128 selects it.)  Without link fields (planar: a short per-sample body, so the per-iteration
+            // block phases — b = P mu, softmax, update — weigh more and 80 registers are not needed) 128-thread CTAs at 10 CTAs/SM
+            // and 48 registers give 2.23 -> 1.81 ms at 4096 x 4 x 256; grids too small to fill that keep 256 threads.
             const bool light = (CHAIN == 0) && !(P.has_spheres || P.has_self);
-            if (sh.S > 128 && !bs128 && (!light || bs256_forced)) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
+            const bool want128 = bs128 || (light && n_part >= 10L * 148);
+            if (sh.S > 128 && !want128) return launch_iterate_nb<real, 2, N, 256, CHAIN>(sh, P, A, st);
             return launch_iterate_nb<real, 2, N, 128, CHAIN>(sh, P, A, st);
         }
 #ifdef SGPMP_ENABLE_TWO_SAMPLE_PACKING   // measured 4 % slower than dof pairs (register pressure); kept for experiments

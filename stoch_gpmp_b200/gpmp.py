@@ -50,6 +50,9 @@ class GPMPBatch(StochGPMPBatch):
         low = self._lowered
         if low is None:
             raise NotImplementedError("GPMP needs a CostComposite (cost=...)")
+        if not low.sigma_start > 0:
+            # the reference's CostGPTrajectory.get_linear_system is `pass` (cost_functions.py:217-218): GPMP fails on it too
+            raise NotImplementedError("GPMP cannot take CostGPTrajectory (no linear system in the reference either); use CostGP")
         # start/GP/goal part of A^T K A: the prior's closed form evaluated with the COST sigmas
         # (CostGP cost_functions.py:148-168, CostGoalPrior :390-405)
         D, O = prior_blocks(self.traj_len, low.dt, low.sigma_start, low.sigma_gp,

@@ -44,8 +44,12 @@ def _lowered(spec, dev, dtype, B=1):
     from stoch_gpmp_b200.robots import PandaFK
     ta = dict(device=dev, dtype=dtype)
     n, T = spec['n_dof'], spec['T']
-    cl = [CostGP(n, T, torch.tensor(spec['start'], **ta), spec['dt'],
-                 dict(sigma_start=spec['cost_sigma_start'], sigma_gp=spec['cost_sigma_gp']), ta)]
+    if spec.get('cost_sigma_start') is None:
+        from stoch_gpmp_b200.costs.cost_functions import CostGPTrajectory
+        cl = [CostGPTrajectory(n, T, torch.tensor(spec['start'], **ta), spec['dt'], dict(sigma_gp=spec['cost_sigma_gp']), ta)]
+    else:
+        cl = [CostGP(n, T, torch.tensor(spec['start'], **ta), spec['dt'],
+                     dict(sigma_start=spec['cost_sigma_start'], sigma_gp=spec['cost_sigma_gp']), ta)]
     if spec.get('goals') is not None and spec.get('sigma_goal_prior') is not None:
         cl.append(CostGoalPrior(n, T, multi_goal_states=torch.tensor(spec['goals'], **ta), num_particles_per_goal=spec['K'],
                                 num_samples=spec['S'], sigma_goal_prior=spec['sigma_goal_prior'], tensor_args=ta))
@@ -237,7 +241,10 @@ def test_cost_terms_match_reference(name, cuda):
         costs, terms = _ops().cost(sh, low.desc(spec['temperature'], sp), tab, xs, mu, want_terms=True)
         terms = terms.cpu().numpy()[:, 0]
         costs = costs.cpu().numpy()[0]
-        assert rel(terms[0], g[pre + 'term_start']) < tol
+        if pre + 'term_start' in g.files:
+            assert rel(terms[0], g[pre + 'term_start']) < tol
+        else:
+            assert not terms[0].any()                      # CostGPTrajectory: no start factor
         assert rel(terms[0] + terms[1], g[pre + 'term_gp']) < tol
         if 'goals' in g.files and spec['sigma_goal_prior']:
             assert rel(terms[2], g[pre + 'term_goal']) < tol
