@@ -82,6 +82,23 @@ def main():
         ops._lib.check(ops._lib.load().sgpmp_sample(ops.C.byref(sh), ops._ptr(tab), ops._ptr(means), ops._ptr(eps), 1, 0, ops._ptr(out), None, ops._stream()), "k2")
     report("K2 sample (injected eps)", timeit(k2_inj), bytes_=2 * ntraj * M * 4, note="reads eps + writes samples")
 
+    # K2 as the reference formulates it (dense L @ eps), on the tensor cores: the comparison point for the banded recurrence
+    if B * NP <= 65535 and T % 2 == 0:
+        L1 = ops.prior_dense_L(tab, 1, torch.float32)
+        bf16_tf0 = (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1663.8) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1663.8)
+
+        def k2_dense():
+            ops._lib.check(ops._lib.load().sgpmp_sample_dense_tc(ops.C.byref(sh), ops._ptr(L1), ops._ptr(means), ops._ptr(eps), ops._ptr(out), ops._stream()), "k2d")
+        ms = timeit(k2_dense)
+        useful = ntraj * n * 2.0 * (2 * T) ** 2 / 2          # lower-triangular L: half of the dense product is structurally zero
+        tiles_m = (2 * T + 127) // 128
+        issued = 3.0 * B * NP * n * ((S + 127) // 128) * sum(2.0 * 128 * 128 * (min(2 * T, 128 * (m + 1)) + 31) // 32 * 32 for m in range(tiles_m))
+        print(json.dumps({"kernel": "K2 sample, dense-L variant (tcgen05 kind::tf32, 3xTF32, injected eps)", "workload": w["name"], "problems": B,
+                          "traj_samples": ntraj, "ms": ms, "issued_tflops": issued / (ms * 1e-3) / 1e12, "tf32_peak_tflops_est": bf16_tf0 / 2,
+                          "frac_of_tf32_peak_issued": issued / (ms * 1e-3) / 1e12 / (bf16_tf0 / 2),
+                          "algorithmic_bytes": 2 * ntraj * M * 4, "achieved_gbs": 2 * ntraj * M * 4 / (ms * 1e-3) / 1e9, "frac_of_hbm": 2 * ntraj * M * 4 / (ms * 1e-3) / 1e9 / hbm,
+                          "note": "same inputs and outputs as 'K2 sample (injected eps)' above; %d flop per sample issued against %d for the banded recurrence" % (round(issued / ntraj), 16 * T * n)}), flush=True)
+
     costs = torch.empty(B, NP, S, device=dev)
 
     def k3():

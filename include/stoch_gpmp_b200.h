@@ -258,6 +258,13 @@ int sgpmp_gpmp_step(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, c
                     void* means, void* d_theta, void* costs, void* workspace, int64_t workspace_bytes,
                     int32_t* not_pd, void* stream);
 
+/* K2, dense-L variant on the tensor cores (the reference's formulation: loc + L @ eps, multivariate_normal.py:251-254, per DoF
+ * because the precision decouples; SURVEY §8(d) "second K2 variant"): samples = means + L1 eps_in with L1 [2T, 2T] the per-DoF
+ * scale_tril (sgpmp_prior_dense_L with n_dof = 1), tcgen05 kind::tf32 with a 3xTF32 split.  fp32 only; eps_in is required.
+ * Not the product path (32x the flops of the banded recurrence) — a measured comparison point, see bench_kernels.py. */
+int sgpmp_sample_dense_tc(const sgpmp_shape_t* shape, const void* L1, const void* means, const void* eps_in,
+                          void* samples, void* stream);
+
 /* Weighted sample covariance of every particle (diagnostic; NO reference counterpart — the reference keeps Sigma^-1 fixed,
  * planner.py:226; asked for by the north-star next to the weighted-mean update of planner.py:263-275):
  *   cov[b,p] = sum_s w[b,p,s] (x_s - mu)(x_s - mu)^T      samples [B,NP,T,d,S] (S-minor), means [B,NP,T,d], weights [B,NP,S]

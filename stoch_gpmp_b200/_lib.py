@@ -70,6 +70,7 @@ SIGNATURES = {
     "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_gpmp_workspace_bytes": (_i64, [_SP, _i32]),
     "sgpmp_gpmp_step": (C.c_int, [_SP, _DP, _vp, _vp, _dbl, _i32, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "sgpmp_sample_dense_tc": (C.c_int, [_SP, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_weighted_cov": (C.c_int, [_SP, _vp, _vp, _vp, _vp, _i32, _vp]),
     "sgpmp_probe": (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
 }

@@ -19,50 +19,17 @@
 // The operation is tiny (2 M^2 S = 0.8 GFLOP per Panda particle) and its operands need arithmetic before they reach the tensor
 // core (mean subtraction, weighting, TF32 split), so the staging is done by the CTA's threads rather than by TMA.
 // fp64: CUDA-core kernel, one thread per entry (fp64 planners are parity configurations).
-#include "sgpmp_common.cuh"
+#include "sgpmp_tc.cuh"
 
 namespace sgpmp {
 
-constexpr int COV_TILE = 128;     // rows of the A block = rows of the B block = UMMA M = UMMA N
-constexpr int COV_KC = 32;        // samples per chunk (4 UMMA K steps of 8 tf32)
-// A core matrix is 8 rows x 16 bytes, contiguous (128 B).  K-adjacent core matrices are placed 144 B apart (16 B of padding):
-// the 8 lanes that stage one row write 16-byte pieces 144 B apart = 8 different bank groups (128 B apart they would all
-// hit the same four banks, an 8-way conflict on every STS.128).
-constexpr uint32_t COV_LBO = 144;                    // bytes between core matrices adjacent in K
-constexpr uint32_t COV_SBO = (COV_KC / 4) * COV_LBO; // bytes between 8-row groups: all K core matrices of a group are contiguous
-constexpr int COV_OP_BYTES = (COV_TILE / 8) * COV_SBO;   // one operand buffer (18 KiB)
-constexpr int COV_THREADS = 256;                     // 8 warps stage; one thread issues the MMAs; all 8 warps drain TMEM
-constexpr int COV_STAGES = 2;                        // shared-memory stages: chunk c+1 is staged while the MMAs of chunk c run
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, no swizzle, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                 // start address, bits [0,14)
-    d |= (uint64_t)((COV_LBO >> 4) & 0x3FFF) << 16;         // leading-dimension byte offset, bits [16,30)
-    d |= (uint64_t)((COV_SBO >> 4) & 0x3FFF) << 32;         // stride-dimension byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                                 // descriptor version 1
-    return d;                                               // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 128, M = 128
-constexpr uint32_t COV_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COV_TILE >> 3) << 17) | ((uint32_t)(COV_TILE >> 4) << 24);
-
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}\n" ::"r"(mbar), "r"(parity) : "memory");
-}
+using tc::smem_u32;
+constexpr int COV_TILE = tc::TILE;     // rows of the A block = rows of the B block = UMMA M = UMMA N
+constexpr int COV_KC = tc::KC;         // samples per chunk (4 UMMA K steps of 8 tf32)
+constexpr uint32_t COV_LBO = tc::LBO, COV_SBO = tc::SBO;
+constexpr int COV_OP_BYTES = tc::OP_BYTES;
+constexpr int COV_THREADS = 256;       // 8 warps stage; one thread issues the MMAs; all 8 warps drain TMEM
+constexpr int COV_STAGES = 2;          // shared-memory stages: chunk c+1 is staged while the MMAs of chunk c run
 
 __global__ void __launch_bounds__(COV_THREADS, 1)
 weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ samples, const float* __restrict__ means,
@@ -84,18 +51,14 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
     const float* w = weights + (size_t)bp * S;
     float* C = cov + (size_t)bp * M * M;
 
-    if (warp == 0) {      // TMEM: 128 columns x 128 lanes of fp32 for the accumulator tile
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 0) tc::tmem_alloc128(&tmem_base_s);      // TMEM: 128 columns x 128 lanes of fp32 for the accumulator tile
     if (tid == 0) {
-        for (int k = 0; k < COV_STAGES; ++k)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[k])), "r"(1) : "memory");
+        for (int k = 0; k < COV_STAGES; ++k) tc::mbar_init(&mbar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc::fence_before_sync();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc::fence_after_sync();
     const uint32_t tmem_acc = tmem_base_s;
 
     // Staging map: thread = (row group rg = tid / 8, K block kb = tid % 8).  In pass it the thread handles row
@@ -145,8 +108,8 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
             }
         }
         if (c >= COV_STAGES) {      // (the global loads above are already in flight)
-            mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((c / COV_STAGES) - 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc::mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((c / COV_STAGES) - 1) & 1));
+            tc::fence_after_sync();
         }
 #pragma unroll
         for (int op = 0; op < 2; ++op) {
@@ -154,49 +117,32 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int r = RPP * it + rg;
-                const uint32_t off = (uint32_t)(r >> 3) * COV_SBO + (uint32_t)(r & 7) * 16 + (uint32_t)kb * COV_LBO;
+                const uint32_t off = tc::op_offset(r, kb);
                 const float x4[4] = {v[op][it].x, v[op][it].y, v[op][it].z, v[op][it].w};
                 float hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float y = sw[q] * (x4[q] - m[op][it]);       // rows >= M hold x = m = 0, samples >= S have sw = 0
-                    hi[q] = to_tf32(y);
-                    lo[q] = to_tf32(y - hi[q]);
+                    hi[q] = tc::to_tf32(y);
+                    lo[q] = tc::to_tf32(y - hi[q]);
                 }
                 *reinterpret_cast<float4*>((op ? b_hi : a_hi) + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>((op ? b_lo : a_lo) + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+        tc::fence_async_smem();                  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncthreads();
-        // ---- one thread issues the MMAs of this chunk and commits them to the mbarrier -------------------------------
+        // ---- one thread issues the MMAs of this chunk and commits them to the stage's mbarrier -----------------------
         if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc::fence_after_sync();
             const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo);
-            const uint32_t sb_hi = same ? sa_hi : smem_u32(b_hi), sb_lo = same ? sa_lo : smem_u32(b_lo);
-#pragma unroll
-            for (int kk = 0; kk < COV_KC / 8; ++kk) {
-                const uint32_t adv = (uint32_t)kk * 2 * COV_LBO;          // 8 tf32 = 2 core matrices along K
-                const uint64_t dah = umma_smem_desc(sa_hi + adv), dal = umma_smem_desc(sa_lo + adv);
-                const uint64_t dbh = umma_smem_desc(sb_hi + adv), dbl = umma_smem_desc(sb_lo + adv);
-                const uint32_t acc0 = (c > 0 || kk > 0) ? 1u : 0u;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                             ::"r"(tmem_acc), "l"(dah), "l"(dbh), "r"(COV_IDESC), "r"(acc0) : "memory");
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                             ::"r"(tmem_acc), "l"(dah), "l"(dbl), "r"(COV_IDESC), "r"(1u) : "memory");
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                             ::"r"(tmem_acc), "l"(dal), "l"(dbh), "r"(COV_IDESC), "r"(1u) : "memory");
-            }
-            // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
+            tc::mma_chunk_3xtf32(tmem_acc, sa_hi, sa_lo, same ? sa_hi : smem_u32(b_hi), same ? sa_lo : smem_u32(b_lo), c == 0);
+            tc::mma_commit(&mbar[stg]);
         }
     }
     // the last commit covers every MMA issued before it
-    mbar_wait(smem_u32(&mbar[(n_chunks - 1) % COV_STAGES]), (uint32_t)(((n_chunks - 1) / COV_STAGES) & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc::mbar_wait(smem_u32(&mbar[(n_chunks - 1) % COV_STAGES]), (uint32_t)(((n_chunks - 1) / COV_STAGES) & 1));
+    tc::fence_after_sync();
     // ---- epilogue: TMEM -> registers -> C.  A warp may read the TMEM lanes [32 (w % 4), 32 (w % 4) + 32) = rows i0 + 32 (w % 4) +
     // lane; warps 0-3 take the column blocks 0 and 1, warps 4-7 the blocks 2 and 3 ---------------------------------------------
     const int lane_grp = warp & 3;
@@ -205,17 +151,7 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
 #pragma unroll 1
     for (int cb = (warp >> 2) * CB_PER_WARP; cb < (warp >> 2) * CB_PER_WARP + CB_PER_WARP; ++cb) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cb * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc::tmem_load32(tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cb * 32), r);
         if (row < M) {
             const int c0 = j0 + cb * 32;
             if ((M & 3) == 0 && c0 + 32 <= M) {
@@ -235,9 +171,9 @@ weighted_cov_tc_kernel(int M, int S, int tiles, const float* __restrict__ sample
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128) : "memory");
+    if (warp == 0) tc::tmem_free128(tmem_acc);
 }
 
 // fp64 (and cross-check) kernel on the CUDA cores: one thread per entry of C

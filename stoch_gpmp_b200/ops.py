@@ -250,3 +250,17 @@ def weighted_cov(shape, samples, means, weights, tensor_cores=True):
         _lib.check(lib.sgpmp_weighted_cov(C.byref(shape), _ptr(samples), _ptr(means), _ptr(weights), _ptr(cov),
                                           1 if tensor_cores else 0, _stream()), "sgpmp_weighted_cov")
     return cov
+
+
+def sample_dense_tc(shape, tables, means, eps_in):
+    """K2 as the reference formulates it — x = mu + L eps with the dense per-DoF scale_tril — on the tcgen05 tensor cores
+    (3xTF32).  A measured comparison point for the banded recurrence of `sample()`, not the product path.  fp32, eps required."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    _req(means, "means", torch.float32, (B, NP, T, d))
+    _req(eps_in, "eps_in", torch.float32, (B, NP, T, d, S))
+    L1 = prior_dense_L(tables, 1, torch.float32)                      # [2T, 2T]
+    out = torch.empty_like(eps_in)
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_sample_dense_tc(C.byref(shape), _ptr(L1), _ptr(means), _ptr(eps_in), _ptr(out), _stream()), "sgpmp_sample_dense_tc")
+    return out

@@ -722,3 +722,20 @@ def test_planner_weighted_covariance(cuda):
     Y = (x - mu[:, None]).reshape(x.shape[0], x.shape[1], -1)
     want = np.einsum('psi,ps,psj->pij', Y, w, Y)
     assert rel(cov, want) < 2e-5
+
+
+@pytest.mark.parametrize("n,T,S,NP", [(7, 64, 512, 2), (2, 64, 256, 3), (3, 10, 40, 2), (2, 100, 130, 1)])
+def test_sample_dense_tensor_cores_equals_banded(n, T, S, NP, cuda):
+    """The dense-L sampling variant (x = mu + L eps as a per-DoF GEMM on tcgen05, 3xTF32) against the banded recurrence of K2
+    on the same eps: full tile (2T = 128), ragged S, T not filling a tile, and two row tiles (2T = 200)."""
+    rs = np.random.RandomState(n + T)
+    spec = dict(T=T, dt=0.05, goals=np.zeros((1, 2 * n)), sigma_start_sample=0.5, sigma_gp_sample=0.8, sigma_goal_sample=0.5)
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(1, NP, 1, S, T, n, torch.float32)
+    mu = torch.tensor(rs.normal(0, 1, (1, NP, T, 2 * n)), device=cuda, dtype=torch.float32)
+    eps = torch.tensor(rs.normal(0, 1, (1, NP, T, 2 * n, S)), device=cuda, dtype=torch.float32)
+    banded = _ops().sample(sh, tab, mu, eps_in=eps)
+    dense = _ops().sample_dense_tc(sh, tab, mu, eps)
+    y_b = (banded - mu.unsqueeze(-1)).double()
+    y_d = (dense - mu.unsqueeze(-1)).double()
+    assert float((y_b - y_d).abs().max() / y_b.abs().max()) < 1e-5
