@@ -324,23 +324,30 @@ gpmp_assemble_kernel(const __grid_constant__ CostParams<double> P, const __grid_
     }
 }
 
-// One warp per particle; lane i owns row i of the current d x d block (d <= 32).
+// One warp per particle — or per TWO particles when d <= 16 (SUB = 2: lanes 0-15 and 16-31 each own one particle; with the
+// Panda's d = 14 that fills 28 of 32 lanes instead of 14).  Lane i of a half owns row i of the current d x d block.
 template <typename real, int N, int WPB>
 __global__ void __launch_bounds__(32 * WPB)
 gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
     constexpr int d = 2 * N, LD = d + 1;
     static_assert(d <= 32, "one lane per row of a pivot block");
-    __shared__ double Ssm[WPB][d * LD], Wsm[WPB][d * LD], zsm[WPB][d], xsm[WPB][d];
+    constexpr int SUB = (d <= 16) ? 2 : 1;
+    constexpr int HALF = 32 / SUB;
+    __shared__ double Ssm[WPB * SUB][d * LD], Wsm[WPB * SUB][d * LD], zsm[WPB * SUB][d], xsm[WPB * SUB][d];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bp = blockIdx.x * WPB + warp;
-    if (bp >= n_particles) return;
-    double* S = Ssm[warp];
-    double* W = Wsm[warp];
-    double* z = zsm[warp];
-    double* xn = xsm[warp];
+    const int sub = lane / HALF, src0 = sub * HALF;            // shuffles read lane (src0 + j) of the own half
+    if ((blockIdx.x * WPB + warp) * SUB >= n_particles) return;
+    const int slot = warp * SUB + sub;
+    const int bp_raw = (blockIdx.x * WPB + warp) * SUB + sub;
+    const bool live = bp_raw < n_particles;                    // an odd particle count leaves the last upper half idle
+    const int bp = live ? bp_raw : n_particles - 1;
+    double* S = Ssm[slot];
+    double* W = Wsm[slot];
+    double* z = zsm[slot];
+    double* xn = xsm[slot];
     const int T = A.T, b = bp / A.NP;
-    const int i = lane, ai = i / N, ii = i - ai * N;       // row i = (pos|vel, dof)
-    const bool row = i < d;
+    const int i = lane - src0, ai = i / N, ii = i - ai * N;    // row i = (pos|vel, dof)
+    const bool row = live && i < d;
     const real* means = reinterpret_cast<const real*>(A.means_in) + (size_t)bp * T * d;
     real* mout = reinterpret_cast<real*>(A.means_out) + (size_t)bp * T * d;
     real* dth = A.d_theta ? reinterpret_cast<real*>(A.d_theta) + (size_t)bp * T * d : nullptr;
@@ -386,15 +393,15 @@ gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
                 v = S[i * LD + j];
                 for (int k = 0; k < j; ++k) v -= S[i * LD + k] * S[j * LD + k];
             }
-            const double piv = __shfl_sync(0xffffffffu, v, j);
-            if (!(piv > 0.0) && !bad) bad = 1 + t;
+            const double piv = __shfl_sync(0xffffffffu, v, src0 + j);
+            if (live && !(piv > 0.0) && !bad) bad = 1 + t;
             const double lj = sqrt(piv);
             if (row && i >= j) S[i * LD + j] = (i == j) ? lj : v / lj;
             __syncwarp();
         }
         // ---- forward substitution z_t = L^-1 rhs ---------------------------------------------------------------------
         for (int j = 0; j < d; ++j) {
-            const double zj = __shfl_sync(0xffffffffu, rhs, j) / S[j * LD + j];
+            const double zj = __shfl_sync(0xffffffffu, rhs, src0 + j) / S[j * LD + j];
             if (row && i > j) rhs -= S[i * LD + j] * zj;
             if (i == j) rhs = zj;
         }
@@ -445,7 +452,7 @@ gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
             }
             __syncwarp();
             for (int j = d - 1; j >= 0; --j) {
-                const double xj = __shfl_sync(0xffffffffu, rhs, j) / S[j * LD + j];
+                const double xj = __shfl_sync(0xffffffffu, rhs, src0 + j) / S[j * LD + j];
                 if (row && i < j) rhs -= S[j * LD + i] * xj;
                 if (i == j) rhs = xj;
             }
@@ -458,7 +465,7 @@ gpmp_solve_kernel(const __grid_constant__ GpmpArgs A, int n_particles) {
             __syncwarp();
         }
     }
-    if (lane == 0) A.not_pd[bp] = bad;
+    if (live && i == 0) A.not_pd[bp] = bad;
 }
 
 template <typename real, int N>
@@ -476,7 +483,8 @@ static int launch_gpmp_n(const sgpmp_shape_t& sh, const CostParams<double>& P, G
         for (int it = 0; it < n_iters; ++it) {
             gpmp_assemble_kernel<real, N><<<BP, 128, smem, st>>>(P, A);
             SGPMP_CHECK_LAUNCH("sgpmp_gpmp_step(assemble)");
-            gpmp_solve_kernel<real, N, WPB><<<(BP + WPB - 1) / WPB, 32 * WPB, 0, st>>>(A, BP);
+            constexpr int PPC = WPB * ((d <= 16) ? 2 : 1);       // particles per CTA
+            gpmp_solve_kernel<real, N, WPB><<<(BP + PPC - 1) / PPC, 32 * WPB, 0, st>>>(A, BP);
             SGPMP_CHECK_LAUNCH("sgpmp_gpmp_step(solve)");
             A.means_in = A.means_out;
         }
