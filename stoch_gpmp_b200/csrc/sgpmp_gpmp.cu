@@ -24,6 +24,8 @@
 //                         d = diag(l)^-1 z.  Reproduced as is (oracle/gpmp.py::solve, pinned by tests/golden/gpmp_*).
 #include <math.h>
 
+#include <algorithm>
+
 #include "sgpmp_common.cuh"
 #include "sgpmp_cost.cuh"
 
@@ -481,7 +483,9 @@ static int launch_gpmp_n(const sgpmp_shape_t& sh, const CostParams<double>& P, G
         if (smem > 48 * 1024) cudaFuncSetAttribute(gpmp_assemble_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         constexpr int WPB = (d <= 16) ? 4 : 1;       // static shared memory: WPB * (2 d (d+1) + 2 d) doubles
         for (int it = 0; it < n_iters; ++it) {
-            gpmp_assemble_kernel<real, N><<<BP, 128, smem, st>>>(P, A);
+            // one thread per time step: no more threads than steps (T = 64: 64-thread CTAs, twice the resident CTAs per SM)
+            const int abs_ = std::min(128, ((sh.T + 31) / 32) * 32);
+            gpmp_assemble_kernel<real, N><<<BP, abs_, smem, st>>>(P, A);
             SGPMP_CHECK_LAUNCH("sgpmp_gpmp_step(assemble)");
             constexpr int PPC = WPB * ((d <= 16) ? 2 : 1);       // particles per CTA
             gpmp_solve_kernel<real, N, WPB><<<(BP + PPC - 1) / PPC, 32 * WPB, 0, st>>>(A, BP);
