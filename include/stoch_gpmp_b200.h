@@ -224,6 +224,17 @@ int sgpmp_iterate(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, con
                   void* means, void* means_pre, void* samples, void* costs, void* weights, void* grad,
                   void* stream);
 
+/* The same loop for FEW problems (the reference's own use: one problem per planner), where the fused kernel's thread-per-sample
+ * mapping leaves the GPU idle: per iteration three short launches — sgpmp_sample (thread per sample and DoF), a cost kernel with
+ * thread per (sample, time slice), sgpmp_update with the state rows of a particle divided over CTAs — all n_iters iterations
+ * enqueued by this one call.  Same arguments and results as sgpmp_iterate (same Philox stream; costs agree to the fp rounding
+ * of the per-step sum), except that the sample workspace [B,NP,T,d,S] and costs [B,NP,S] are REQUIRED: samples_ws holds the
+ * last iteration's samples on return. */
+int sgpmp_iterate_lowlat(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+                         double step_size, int32_t n_iters, const void* eps_in, uint64_t seed, uint32_t draw0,
+                         void* means, void* means_pre, void* samples_ws, void* costs, void* weights, void* grad,
+                         void* stream);
+
 /* Split-particle mode (one problem's samples sharded over ranks).  Local statistics of
  * this rank's S_local samples per particle:  stats[B,NP, 2 + M] = (m, Z, A[M]) with
  *   m = max_s(-c_s/tau), Z = sum_s exp(-c_s/tau - m), A = sum_s exp(-c_s/tau - m) eps_s.

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sgpmp_fk_link_positions": (C.c_int, [_DP, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sgpmp_update": (C.c_int, [_SP, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_iterate": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgpmp_iterate_lowlat": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_local_stats": (C.c_int, [_SP, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_gpmp_workspace_bytes": (_i64, [_SP, _i32]),

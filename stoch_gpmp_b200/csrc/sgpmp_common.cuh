@@ -73,6 +73,14 @@ struct CostParams {
 template <typename real>
 int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostParams<real>& out);
 
+// cross-file launchers used by the low-latency iteration (sgpmp_lowlat.cu)
+int sample_launch(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in, uint64_t seed,
+                  uint32_t draw, void* samples, cudaStream_t st);
+int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
+                   const void* means, void* costs, cudaStream_t st);
+int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
+                  void* grad, void* weights, int row_chunks, cudaStream_t st);
+
 inline bool shape_ok(const sgpmp_shape_t* s) {
     return s && s->B > 0 && s->G > 0 && s->K > 0 && s->S > 0 && s->T >= 2 && s->n_dof > 0 && s->n_dof <= 255 &&
            (s->dtype == SGPMP_F32 || s->dtype == SGPMP_F64);

@@ -201,6 +201,126 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     }
 }
 
+// Low-latency form of K3 for FEW trajectories (one planning problem): a trajectory's time steps are spread over the TW warps
+// of a CTA (lane = sample, warp w takes t = w, w + TW, ...), so B*NP*S*TW threads work instead of B*NP*S — with one problem
+// (2,048 samples) the thread-per-sample kernel leaves most of the GPU idle and every thread walks 64 dependent steps.
+// Same per-step arithmetic (TrajCost::step on a fresh object with x_{t-1} preset); the per-step contributions are summed in a
+// fixed order (warp 0..TW-1), so results are deterministic and agree with cost_kernel to fp32 rounding of the sum.
+template <typename real, int N, int CHAIN, int TW>
+__global__ void __launch_bounds__(32 * TW)
+cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int T,
+               const double* __restrict__ tab, const real* __restrict__ samples, const real* __restrict__ means,
+               real* __restrict__ costs) {
+    constexpr int d = 2 * N;
+    constexpr int DP = (d + 3) & ~3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* sph = reinterpret_cast<real*>(smem_raw);
+    real* bvec = sph + SPH_SMEM;                                         // [T][DP]
+    double* tabDO = reinterpret_cast<double*>(bvec + (size_t)T * DP);    // [T][7]
+    real* mu = reinterpret_cast<real*>(tabDO + (size_t)T * 7);           // [T][d]
+    real* start = mu + (size_t)T * d;
+    real* goal = start + d;
+    real* part = goal + d;                                               // [TW][32]
+    const int NP = G * K;
+    const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
+    for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
+        tabDO[k] = tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + SGPMP_TAB_D11 + (k % 7)];
+    for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
+    stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
+    double mub_part = 0.0;
+    for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
+        const int t = k / N, i = k - t * N;
+        mub_part += precision_times_row<real>(tabDO, mu, T, N, t, i, &bvec[t * DP + i], &bvec[t * DP + N + i]);
+    }
+    __shared__ double red64[32];
+    const real mub = (real)block_sum_f64(mub_part, red64);
+    CostSmem<real> sm;
+    sm.start = start; sm.goal = goal; sm.bvec = bvec; sm.sph = sph;
+    sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
+    sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
+    sm.mub = mub;
+    sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+    sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.y * 32 + lane;
+    real acc = 0;
+    if (s < S) {
+        const real* xs = samples + (size_t)bp * T * d * S + s;
+        for (int t = w; t < T; t += TW) {
+            TrajCost<real, N, CHAIN> tc;
+            tc.begin();
+            real x[d], y[d];
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                x[j] = xs[((size_t)t * d + j) * S];
+                y[j] = x[j] - mu[t * d + j];
+                tc.xp[j] = t > 0 ? xs[((size_t)(t - 1) * d + j) * S] : (real)0;
+            }
+            tc.step(P, sm, t, T, x, y, y + N, bvec + t * DP);
+            real v = tc.partial(P, sm, T, t);
+            if (t == T - 1 && P.has_ee) {
+                real q[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) q[i] = x[i];
+                v += ee_se3_cost<real, N>(P, q) * P.ee_w;
+            }
+            acc += v;
+        }
+    }
+    part[w * 32 + lane] = acc;
+    __syncthreads();
+    if (w == 0 && s < S) {
+        real tot = 0;
+        for (int k = 0; k < TW; ++k) tot += part[k * 32 + lane];
+        costs[(size_t)bp * S + s] = tot;
+    }
+}
+
+template <typename real, int N, int CHAIN>
+static int launch_cost_st_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
+                            const void* means, void* costs, cudaStream_t st) {
+    constexpr int TW = 16;
+    const int NP = sh.G * sh.K, d = 2 * N;
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + 31) / 32));
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM + 32 * TW) * sizeof(real);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) { set_error("sgpmp_iterate_lowlat: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
+        cudaFuncSetAttribute(cost_st_kernel<real, N, CHAIN, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    cost_st_kernel<real, N, CHAIN, TW><<<grid, 32 * TW, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
+                                                                  (const real*)means, (real*)costs);
+    SGPMP_CHECK_LAUNCH("sgpmp_iterate_lowlat(cost)");
+    return SGPMP_OK;
+}
+
+template <typename real>
+static int launch_cost_st(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
+                          const void* means, void* costs, cudaStream_t st) {
+    CostParams<real> P;
+    int rc = lower_cost_desc<real>(sh, desc, P);
+    if (rc != SGPMP_OK) return rc;
+    if constexpr (sizeof(real) == 4) {
+        if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof))
+            return P.has_self ? launch_cost_st_n<real, 7, 2>(sh, P, tables, samples, means, costs, st)
+                              : launch_cost_st_n<real, 7, 1>(sh, P, tables, samples, means, costs, st);
+    }
+    switch (sh.n_dof) {
+#define SGPMP_DOF_CASE(N) case N: return launch_cost_st_n<real, N, 0>(sh, P, tables, samples, means, costs, st);
+#include "sgpmp_dof_list.inc"
+#undef SGPMP_DOF_CASE
+        default:
+            set_error("sgpmp_iterate_lowlat: n_dof=%d is not instantiated (see sgpmp_dof_list.inc)", sh.n_dof);
+            return SGPMP_ERR_UNSUPPORTED;
+    }
+}
+
+int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
+                   const void* means, void* costs, cudaStream_t st) {
+    if (sh.dtype == SGPMP_F32) return launch_cost_st<float>(sh, desc, tables, samples, means, costs, st);
+    return launch_cost_st<double>(sh, desc, tables, samples, means, costs, st);
+}
+
 // Link-frame origins of N_cfg configurations: q [n_cfg][N] -> pos [n_cfg][L][3].  Same FK code as the cost
 // kernel; used for known-answer tests and collision-freeness checks of final plans.
 template <typename real, int N>

@@ -502,6 +502,22 @@ struct TrajCost {
             }
         }
     }
+    // Contribution of ONE time step to the total (everything above is linear in the per-step accumulators): used by the
+    // low-latency cost kernel, where a trajectory's time steps are spread over threads.  Call after begin() + step(t) on a fresh
+    // object (xp preset to x_{t-1}); the q-independent constants and mu^T b are added by the thread that owns t = T-1.
+    __device__ __forceinline__ V partial(const CostParams<real>& P, const CostSmem<real>& sm, int T, int t) const {
+        V coll = c_coll + map_pending, self = c_self, is = c_is;
+        if constexpr (VT<V>::W == 1) coll = coll + (real)map_pending_u8;
+        if (t == T - 1) {
+            if (CHAIN >= 1) {
+                coll = coll + (real)(T - 1) * sm.coll_const;
+                self = self + (real)(T - 1) * sm.self_const;
+            }
+            is = is + sm.mub;
+        }
+        return ((((c_start * P.inv_sig_start2 + c_gp) + c_goal * P.inv_sig_goal2) + self * P.self_w_coll) +
+                coll * (P.has_map ? P.map_w_coll : P.sphere_w_coll)) + is * P.temperature;
+    }
     // summation order of the shipped examples' cost lists: CostGP (start + gp), CostGoalPrior, self-collision,
     // obstacle collision, EE goal (examples/panda_environment.py:90), then += IS (planner.py:236)
     __device__ __forceinline__ V total() const { return (((((c_start + c_gp) + c_goal) + c_self) + c_coll) + c_ee) + c_is; }

@@ -72,25 +72,29 @@ update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs,
     const size_t bp = blockIdx.x;
     real m, Z;
     block_softmax<real>(costs + bp * S, S, tau, wsm, red, true, &m, &Z);
-    if (weights)
+    if (weights && blockIdx.y == 0)
         for (int s = threadIdx.x; s < S; s += blockDim.x) weights[bp * S + s] = wsm[s];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const real* xs = samples + bp * (size_t)M * S;
+    // gridDim.y > 1 (few particles): the state rows of a particle are divided over gridDim.y CTAs, each of which recomputes
+    // the (cheap) softmax — with one planning problem a CTA per particle would leave all but NP SMs idle
+    const int rows_per = ((M + (int)gridDim.y - 1) / (int)gridDim.y + 3) & ~3;
+    const int row_lo = (int)blockIdx.y * rows_per, row_hi = min(M, row_lo + rows_per);
     // four rows per warp pass: four independent load streams in flight (the kernel is HBM-latency bound otherwise)
-    for (int r0 = warp * 4; r0 < M; r0 += nw * 4) {
+    for (int r0 = row_lo + warp * 4; r0 < row_hi; r0 += nw * 4) {
         real acc[4] = {0, 0, 0, 0}, mu[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) mu[q] = (r0 + q < M) ? means[bp * M + r0 + q] : (real)0;
+        for (int q = 0; q < 4; ++q) mu[q] = (r0 + q < row_hi) ? means[bp * M + r0 + q] : (real)0;
         for (int s = lane; s < S; s += 32) {
             const real w = wsm[s];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (r0 + q < M) acc[q] += w * (xs[(size_t)(r0 + q) * S + s] - mu[q]);
+                if (r0 + q < row_hi) acc[q] += w * (xs[(size_t)(r0 + q) * S + s] - mu[q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const real a = warp_sum(acc[q]);
-            if (lane == 0 && r0 + q < M) {
+            if (lane == 0 && r0 + q < row_hi) {
                 if (grad) grad[bp * M + r0 + q] = a;
                 means[bp * M + r0 + q] = mu[q] + step * a;
             }
@@ -149,11 +153,11 @@ __global__ void apply_stats_kernel(int n_particles, int T, int n, const double* 
 
 template <typename real>
 static int launch_update(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples,
-                         void* means, void* grad, void* weights, cudaStream_t st) {
+                         void* means, void* grad, void* weights, cudaStream_t st, int row_chunks = 1) {
     const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
     const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
     if (smem > 48 * 1024) cudaFuncSetAttribute(update_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    update_kernel<real><<<(unsigned)(sh.B * NP), 256, smem, st>>>(sh.S, M, (real)tau, (real)step, (const real*)costs,
+    update_kernel<real><<<dim3((unsigned)(sh.B * NP), (unsigned)row_chunks), 256, smem, st>>>(sh.S, M, (real)tau, (real)step, (const real*)costs,
                                                                  (const real*)samples, (real*)means, (real*)grad,
                                                                  (real*)weights);
     SGPMP_CHECK_LAUNCH("sgpmp_update");
@@ -181,6 +185,12 @@ static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, dou
                                                                   (const real*)stats, (real*)means, (real*)grad);
     SGPMP_CHECK_LAUNCH("sgpmp_apply_stats");
     return SGPMP_OK;
+}
+
+int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
+                  void* grad, void* weights, int row_chunks, cudaStream_t st) {
+    if (sh.dtype == SGPMP_F32) return launch_update<float>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks);
+    return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks);
 }
 
 }  // namespace sgpmp

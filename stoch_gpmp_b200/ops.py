@@ -118,7 +118,7 @@ def update(shape, temperature, step_size, costs, samples, means):
 
 
 def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0, draw0=0,
-            want_samples=False, want_costs=True, want_weights=True, want_grad=True, want_means_pre=True):
+            want_samples=False, want_costs=True, want_weights=True, want_grad=True, want_means_pre=True, lowlat=False):
     """Fused loop.  Updates `means` in place.  Returns dict(means_pre, samples, costs, weights, grad) of the
     LAST iteration (entries not requested are None)."""
     lib = _lib.load()
@@ -128,6 +128,21 @@ def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0,
     _req(means, "means", None, (B, NP, T, d))
     if eps_in is not None:
         _req(eps_in, "eps_in", dt, (n_iters, B, NP, T, d, S))
+    if lowlat:
+        # few problems: three short launches per iteration instead of the thread-per-sample fused kernel (csrc/sgpmp_lowlat.cu)
+        out = dict(means_pre=torch.empty_like(means) if want_means_pre else None,
+                   samples=torch.empty(B, NP, T, d, S, dtype=dt, device=dev),
+                   costs=torch.empty(B, NP, S, dtype=dt, device=dev),
+                   weights=torch.empty(B, NP, S, dtype=dt, device=dev) if want_weights else None,
+                   grad=torch.empty_like(means) if want_grad else None)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sgpmp_iterate_lowlat(C.byref(shape), C.byref(desc), _ptr(tables), float(step_size), int(n_iters),
+                                                _ptr(eps_in), seed, draw0, _ptr(means), _ptr(out["means_pre"]), _ptr(out["samples"]),
+                                                _ptr(out["costs"]), _ptr(out["weights"]), _ptr(out["grad"]), _stream()),
+                       "sgpmp_iterate_lowlat")
+        if not want_samples:
+            out["samples"] = None
+        return out
     out = dict(
         means_pre=torch.empty_like(means) if want_means_pre else None,
         samples=torch.empty(B, NP, T, d, S, dtype=dt, device=dev) if want_samples else None,

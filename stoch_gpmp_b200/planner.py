@@ -290,6 +290,19 @@ class StochGPMPBatch:
         self._weights = self._out(w).reshape(*self._out(w).shape, 1, 1)
         return self._out(grad)
 
+    def _lowlat(self):
+        """Few problems (the reference's own use: ONE): the fused kernel's thread-per-sample mapping would leave the GPU idle, so
+        optimize() runs the low-latency form (three short launches per iteration, csrc/sgpmp_lowlat.cu).  $SGPMP_LOWLAT=0/1
+        overrides the choice."""
+        import os
+        env = os.environ.get("SGPMP_LOWLAT")
+        if env is not None:
+            return env != "0"
+        # measured on B200: one Panda problem 91.7 -> 47.5 us per iteration; without link fields (planar) the per-sample work is
+        # so small that three minimum-length launches (~35 us) only tie with the single cluster launch, so the fused form stays
+        heavy = self._lowered is not None and self._lowered.fk is not None
+        return heavy and self.num_problems * self.num_particles * self.num_samples <= 148 * 64
+
     # ---- the hot loop ------------------------------------------------------------------------------------
     def optimize(self, opt_iters=None, debug=False, return_samples=None, _eps=None, **observation):
         """planner.py:277-317.  Runs `opt_iters` iterations in one fused launch and returns the reference's
@@ -316,7 +329,7 @@ class StochGPMPBatch:
             eps = None if _eps is None else _eps[done:done + c].contiguous()
             last_chunk = (done + c == opt_iters)
             out = ops.iterate(sh, desc, self._tables, self.step_size, c, self._means, eps_in=eps, seed=self.seed,
-                              draw0=self._draw, want_samples=bool(return_samples and last_chunk))
+                              draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat())
             self._draw += c
             done += c
             if debug:

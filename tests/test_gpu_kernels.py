@@ -739,3 +739,41 @@ def test_sample_dense_tensor_cores_equals_banded(n, T, S, NP, cuda):
     y_b = (banded - mu.unsqueeze(-1)).double()
     y_d = (dense - mu.unsqueeze(-1)).double()
     assert float((y_b - y_d).abs().max() / y_b.abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ low-latency iteration
+@pytest.mark.parametrize("name", ["panda_soft_f32", "panda_self_f32", "panda_shipped_f32", "planar_soft_f32", "planar_soft_f64", "panda_ee_soft_f64",
+                                  "panda_interp_f64", "panda_sdf_f64"])
+def test_lowlat_iteration_equals_separate_kernels(name, cuda):
+    """sgpmp_iterate_lowlat (few problems: K2 -> cost with thread per (sample, time slice) -> K4 with row chunks, n_iters per call)
+    against K2 -> K3 -> K4: identical samples, costs equal up to the rounding of the per-step sum, and the update reproduced by K4
+    fed the low-latency path's own costs (the softmax amplifies cost rounding, as in the cluster-mode test)."""
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dt)
+    sh = _ops().make_shape(1, spec['G'], spec['K'], spec['S'], spec['T'], spec['n_dof'], dt)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dt).unsqueeze(0) if 'spheres' in spec else None
+    desc = low.desc(spec['temperature'], sp)
+    pre = 'sameL_' if f32 else ''
+    mu = torch.tensor(g[pre + 'it0_means_pre'][None], device=cuda)
+    for it in range(2):
+        xs = _ops().sample(sh, tab, mu, seed=11, draw=it)
+        c = _ops().cost(sh, desc, tab, xs, mu)
+        mu_l = mu.clone()
+        out = _ops().iterate(sh, desc, tab, spec['step_size'], 1, mu_l, seed=11, draw0=it, want_samples=True, lowlat=True)
+        assert torch.equal(out['means_pre'], mu)
+        assert torch.equal(out['samples'], xs)
+        assert float((out['costs'] - c).abs().max() / c.abs().max()) < (2e-6 if f32 else 1e-13)
+        mu_k = mu.clone()
+        grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], out['costs'], xs, mu_k)
+        assert torch.equal(out['weights'], w)
+        assert float((out['grad'] - grad).abs().max() / max(float(grad.abs().max()), 1e-30)) < (1e-5 if f32 else 1e-12)
+        assert float((mu_l - mu_k).abs().max() / mu_k.abs().max()) < (1e-6 if f32 else 1e-13)
+        mu = mu_l
+    # two iterations in ONE call == two calls
+    mu_2 = torch.tensor(g[pre + 'it0_means_pre'][None], device=cuda)
+    _ops().iterate(sh, desc, tab, spec['step_size'], 2, mu_2, seed=11, draw0=0, lowlat=True)
+    assert torch.equal(mu_2, mu)
