@@ -206,7 +206,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
 // (2,048 samples) the thread-per-sample kernel leaves most of the GPU idle and every thread walks 64 dependent steps.
 // Same per-step arithmetic (TrajCost::step on a fresh object with x_{t-1} preset); the per-step contributions are summed in a
 // fixed order (warp 0..TW-1), so results are deterministic and agree with cost_kernel to fp32 rounding of the sum.
-template <typename real, int N, int CHAIN, int TW>
+template <typename real, int N, int CHAIN, int TW, int SL>
 __global__ void __launch_bounds__(32 * TW)
 cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int T,
                const double* __restrict__ tab, const real* __restrict__ samples, const real* __restrict__ means,
@@ -220,7 +220,7 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
     real* mu = reinterpret_cast<real*>(tabDO + (size_t)T * 7);           // [T][d]
     real* start = mu + (size_t)T * d;
     real* goal = start + d;
-    real* part = goal + d;                                               // [TW][32]
+    real* part = goal + d;                                               // [NSL][SL], NSL = 32 TW / SL time slices
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
     for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
@@ -242,12 +242,14 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
     sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
 
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int s = blockIdx.y * 32 + lane;
+    // SL samples per CTA (consecutive threads = consecutive samples), 32 TW / SL time slices: slice w takes t = w, w + NSL, ...
+    constexpr int NSL = 32 * TW / SL;
+    const int lane = threadIdx.x % SL, w = threadIdx.x / SL;
+    const int s = blockIdx.y * SL + lane;
     real acc = 0;
     if (s < S) {
         const real* xs = samples + (size_t)bp * T * d * S + s;
-        for (int t = w; t < T; t += TW) {
+        for (int t = w; t < T; t += NSL) {
             TrajCost<real, N, CHAIN> tc;
             tc.begin();
             real x[d], y[d];
@@ -268,30 +270,40 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
             acc += v;
         }
     }
-    part[w * 32 + lane] = acc;
+    part[w * SL + lane] = acc;
     __syncthreads();
     if (w == 0 && s < S) {
         real tot = 0;
-        for (int k = 0; k < TW; ++k) tot += part[k * 32 + lane];
+        for (int k = 0; k < NSL; ++k) tot += part[k * SL + lane];
         costs[(size_t)bp * S + s] = tot;
     }
+}
+
+template <typename real, int N, int CHAIN, int SL>
+static int launch_cost_st_sl(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
+                             const void* means, void* costs, cudaStream_t st) {
+    constexpr int TW = 16;                // 512 threads: SL samples x (512 / SL) time slices
+    const int NP = sh.G * sh.K, d = 2 * N;
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + SL - 1) / SL));
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM + 32 * TW) * sizeof(real);
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) { set_error("sgpmp_iterate_lowlat: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
+        cudaFuncSetAttribute(cost_st_kernel<real, N, CHAIN, TW, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    cost_st_kernel<real, N, CHAIN, TW, SL><<<grid, 32 * TW, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
+                                                                      (const real*)means, (real*)costs);
+    SGPMP_CHECK_LAUNCH("sgpmp_iterate_lowlat(cost)");
+    return SGPMP_OK;
 }
 
 template <typename real, int N, int CHAIN>
 static int launch_cost_st_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
                             const void* means, void* costs, cudaStream_t st) {
-    constexpr int TW = 16;
-    const int NP = sh.G * sh.K, d = 2 * N;
-    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + 31) / 32));
-    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM + 32 * TW) * sizeof(real);
-    if (smem > 48 * 1024) {
-        if (smem > 227 * 1024) { set_error("sgpmp_iterate_lowlat: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
-        cudaFuncSetAttribute(cost_st_kernel<real, N, CHAIN, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    cost_st_kernel<real, N, CHAIN, TW><<<grid, 32 * TW, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
-                                                                  (const real*)means, (real*)costs);
-    SGPMP_CHECK_LAUNCH("sgpmp_iterate_lowlat(cost)");
-    return SGPMP_OK;
+    // 16 samples x 32 time slices per CTA while that still fits one wave of CTAs (one Panda problem: 128 CTAs, 12.8 us against
+    // 17.2 us); 32 samples x 16 slices beyond (two problems: 37.9 against 41.6 us per iteration)
+    const long ctas16 = (long)sh.B * sh.G * sh.K * ((sh.S + 15) / 16);
+    if (ctas16 <= 148) return launch_cost_st_sl<real, N, CHAIN, 16>(sh, P, tables, samples, means, costs, st);
+    return launch_cost_st_sl<real, N, CHAIN, 32>(sh, P, tables, samples, means, costs, st);
 }
 
 template <typename real>

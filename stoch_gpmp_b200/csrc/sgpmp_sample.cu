@@ -73,6 +73,53 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sampl
     }
 }
 
+// Few-samples variant (one planning problem): one CTA per (particle, DoF, block of 128 samples).  The normals of all T steps are
+// drawn first, by all 256 threads in parallel over (time pair, sample) — the counter-based stream does not care who draws — into
+// shared memory; only then does one thread per sample walk the (cheap) recurrence.  In sample_kernel a thread draws AND walks, i.e.
+// 32 dependent Philox / Box-Muller chains back to back: with 2,048 samples that is a few lone warps (20 us at B = 1).
+// Same stream, same recurrence expressions: bit-identical output.
+template <typename real>
+__global__ void __launch_bounds__(256)
+sample_tiled_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
+                    const real* __restrict__ means, RngKey key, real* __restrict__ samples) {
+    constexpr int SB = 128;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int TP = (T + 1) / 2;
+    real* gh = reinterpret_cast<real*>(smem_raw);       // [T][7]
+    real* mu_i = gh + (size_t)T * 7;                    // [T][2]  (pos, vel) mean of this DoF
+    real* eps = mu_i + (size_t)T * 2;                   // [2 TP][2][SB]
+    const int bp = blockIdx.x, i = blockIdx.y, s0 = blockIdx.z * SB;
+    const int d = 2 * n;
+    for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
+        gh[k] = (real)tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + (k % 7)];
+    for (int k = threadIdx.x; k < T * 2; k += blockDim.x)
+        mu_i[k] = means[(size_t)bp * T * d + (size_t)(k >> 1) * d + (k & 1) * n + i];
+    const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
+    for (int item = threadIdx.x; item < TP * SB; item += blockDim.x) {
+        const int tp = item / SB, sl = item - tp * SB, s = s0 + sl;
+        if (s < S) {
+            real e0, e1, e2, e3;
+            normal4<real>(key, tp, i, sample_gid0 + (uint32_t)s, pgid, e0, e1, e2, e3);
+            real* e = eps + (size_t)(2 * tp) * 2 * SB + sl;
+            e[0] = e0; e[SB] = e1; e[2 * SB] = e2; e[3 * SB] = e3;
+        }
+    }
+    __syncthreads();
+    const int sl = threadIdx.x, s = s0 + sl;
+    if (sl >= SB || s >= S) return;
+    const size_t base = (size_t)bp * T * d * S;
+    real yp = 0, yv = 0;
+    for (int t = 0; t < T; ++t) {
+        const real* r = gh + t * 7;
+        const real e0 = eps[(size_t)t * 2 * SB + sl], e1 = eps[(size_t)t * 2 * SB + SB + sl];
+        const real np_ = r[0] * e0 - (r[3] * yp + r[4] * yv);
+        const real nv_ = r[1] * e0 + r[2] * e1 - (r[5] * yp + r[6] * yv);
+        yp = np_; yv = nv_;
+        samples[base + ((size_t)t * d + i) * S + s] = mu_i[2 * t] + yp;
+        samples[base + ((size_t)t * d + n + i) * S + s] = mu_i[2 * t + 1] + yv;
+    }
+}
+
 // In-kernel-RNG variant for the instantiated DoF counts: one thread per SAMPLE with all DoFs in registers (the
 // mapping of the fused kernel's pass 1).  The generic kernel above spends 44 k instructions per trajectory sample
 // (per-thread index arithmetic for one DoF); this one ~23 k, which moves the kernel from 35 % to >60 % of the HBM
@@ -145,7 +192,20 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
 
 template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
-                         uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st) {
+                         uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false) {
+    if (few && !eps_in && !eps_out) {
+        const int TP = (sh.T + 1) / 2;
+        const size_t smem = ((size_t)sh.T * 9 + (size_t)2 * TP * 2 * 128) * sizeof(real);
+        if (smem <= 200 * 1024 && sh.n_dof <= 65535 && (sh.S + 127) / 128 <= 65535) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const int NPf = sh.G * sh.K;
+            RngKey keyf{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
+            sample_tiled_kernel<real><<<dim3((unsigned)(sh.B * NPf), (unsigned)sh.n_dof, (unsigned)((sh.S + 127) / 128)), 256, smem, st>>>(
+                NPf, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NPf, (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples);
+            SGPMP_CHECK_LAUNCH("sgpmp_sample(tiled)");
+            return SGPMP_OK;
+        }
+    }
     // In-kernel RNG: thread-per-sample kernel for the instantiated DoF counts — when there are enough samples to fill the
     // machine with one thread each.  Few samples with long horizons (C5: one problem, T up to 1024) are latency-bound on the
     // sequential recurrence, so they take the thread-per-(sample, DoF) kernel below: n times the threads, the same stream
@@ -182,8 +242,9 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
 
 int sample_launch(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in, uint64_t seed,
                   uint32_t draw, void* samples, cudaStream_t st) {
-    if (sh.dtype == SGPMP_F32) return launch_sample<float>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st);
-    return launch_sample<double>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st);
+    // called by the low-latency iteration only: few samples, so the tiled kernel (parallel draw, then the recurrence)
+    if (sh.dtype == SGPMP_F32) return launch_sample<float>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true);
+    return launch_sample<double>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true);
 }
 
 }  // namespace sgpmp
