@@ -390,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "ms_per_plan": {"iterations": plan_iters, "single_problem_ms": plan_ms_single,
                             "amortised_over_batch_ms": ms_per_step * plan_iters / B,
-                            "note": "single problem = one StochGPMP (B=1), all iterations enqueued by one optimize() call (Panda: low-latency three-kernel form, planar: one cluster launch)"}}
+                            "note": "single problem = one StochGPMP (B=1), all iterations enqueued by one optimize() call (low-latency three-kernel form, csrc/sgpmp_lowlat.cu)"}}
     print(json.dumps(line), flush=True)
 
 

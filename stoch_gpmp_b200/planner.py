@@ -290,7 +290,7 @@ class StochGPMPBatch:
         self._weights = self._out(w).reshape(*self._out(w).shape, 1, 1)
         return self._out(grad)
 
-    def _lowlat(self):
+    def _lowlat(self, n_iters):
         """Few problems (the reference's own use: ONE): the fused kernel's thread-per-sample mapping would leave the GPU idle, so
         optimize() runs the low-latency form (three short launches per iteration, csrc/sgpmp_lowlat.cu).  $SGPMP_LOWLAT=0/1
         overrides the choice."""
@@ -298,10 +298,12 @@ class StochGPMPBatch:
         env = os.environ.get("SGPMP_LOWLAT")
         if env is not None:
             return env != "0"
-        # measured on B200: one Panda problem 91.7 -> 47.5 us per iteration; without link fields (planar) the per-sample work is
-        # so small that three minimum-length launches (~35 us) only tie with the single cluster launch, so the fused form stays
+        # measured on B200, us per iteration, fused (cluster) form -> low-latency form: one Panda problem 89.9 -> 31.2, one planar
+        # problem 33.3 -> 25.1.  A call that runs a SINGLE cheap (no link fields) iteration is host-bound either way and the fused
+        # form costs the host one launch instead of three (planar example, 501 single-iteration calls: 100 against 142 ms).
+        small = self.num_problems * self.num_particles * self.num_samples <= 148 * 64
         heavy = self._lowered is not None and self._lowered.fk is not None
-        return heavy and self.num_problems * self.num_particles * self.num_samples <= 148 * 64
+        return small and (heavy or n_iters >= 4)
 
     # ---- the hot loop ------------------------------------------------------------------------------------
     def optimize(self, opt_iters=None, debug=False, return_samples=None, _eps=None, **observation):
@@ -329,7 +331,7 @@ class StochGPMPBatch:
             eps = None if _eps is None else _eps[done:done + c].contiguous()
             last_chunk = (done + c == opt_iters)
             out = ops.iterate(sh, desc, self._tables, self.step_size, c, self._means, eps_in=eps, seed=self.seed,
-                              draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat())
+                              draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat(c))
             self._draw += c
             done += c
             if debug:
