@@ -217,6 +217,7 @@ class LoweredCost:
         self._spheres = None
         self._spheres_src = None
         self._desc_cache = None
+        self._ee_key = None
 
     def _need_fk(self, composite, n):
         if not isinstance(composite.FK, SerialChainFK):
@@ -273,9 +274,12 @@ class LoweredCost:
                         arr[k] = a
             self._desc_cache = d
         d.temperature = float(temperature)
-        if self.ee is not None:
-            # the target is re-read on every call: EESE3DistanceField.update_target (fields.py:139-140) may have moved it
+        if self.ee is not None and (not isinstance(self.ee[0].target_H, torch.Tensor) or
+                                    self._ee_key != (id(self.ee[0].target_H), self.ee[0].target_H._version)):
+            # the target is re-read whenever EESE3DistanceField.update_target (fields.py:139-140) replaced the tensor or the tensor
+            # was modified in place (torch version counter) — not on every call: target_matrix() is a device-to-host copy
             fld, sig = self.ee
+            self._ee_key = (id(fld.target_H), fld.target_H._version) if isinstance(fld.target_H, torch.Tensor) else None
             H = fld.target_matrix()
             d.ee_sigma_goal = sig
             for r in range(3):
