@@ -22,6 +22,7 @@
 #include "sgpmp_common.cuh"
 #include "sgpmp_cost.cuh"
 #include "sgpmp_cost_pairs.cuh"
+#include "sgpmp_iterate.cuh"
 #include "sgpmp_rng.cuh"
 
 #ifndef SGPMP_MINB128
@@ -44,22 +45,6 @@ namespace cg = cooperative_groups;
 constexpr int SGPMP_T_UNROLL_C = SGPMP_T_UNROLL;
 
 namespace sgpmp {
-
-template <typename real>
-struct IterArgs {
-    int G, K, S, T, n_iters;
-    uint32_t particle_gid0, sample_gid0;
-    real step;
-    RngKey key;            // key.draw = draw index of iteration 0
-    const double* tab;
-    const real* eps_in;    // [n_iters][B*NP][T][d][S] or null
-    real* means;           // [B*NP][T][d] in/out
-    real* means_pre;       // optional
-    real* samples;         // optional, last iteration
-    real* costs;           // optional, last iteration
-    real* weights;         // optional, last iteration
-    real* grad;            // optional, last iteration
-};
 
 // PACK selects the pass-1 arithmetic:
 //   0  scalar: one sample per thread (fp32 or fp64)
@@ -84,7 +69,6 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
     constexpr int DP = (PACK == 2) ? 2 * VOFF : ((d + 3) & ~3);       // padded row length of mu / b (16-byte aligned rows)
     auto col = [](int j) { return j < N ? j : VOFF + (j - N); };      // external state index -> shared-memory column
     const int T = A.T, S = A.S, G = A.G, K = A.K;
-    const int TP = (T + 1) >> 1;
     const int M = T * d;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* sph = reinterpret_cast<real*>(smem_raw);            // [MAX_SPHERES][8] + coll_const (16-byte aligned)
@@ -130,8 +114,8 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
 
     for (int it = 0; it < A.n_iters; ++it) {
         const bool last = (it == A.n_iters - 1);
-        RngKey key = A.key;
-        key.draw += (uint32_t)it;
+        const RngKey& key = A.key;
+        const uint32_t dro = (uint32_t)it;      // draw index of this iteration = key.draw + it
         const real* eps = A.eps_in ? A.eps_in + ((size_t)it * n_particles + bp) * (size_t)M * S : nullptr;
 
         // ---- b = Sigma^-1 mu (fp64 accumulate) ---------------------------------------------------------
@@ -152,7 +136,7 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             for (int s0 = s_lo + tid; s0 < s_hi; s0 += BS) {
                 TrajCostPairs<N, CHAIN> tc;
                 tc.begin();
-                F2 yp[NP2], yv[NP2], enp[NP2], env[NP2];
+                F2 yp[NP2], yv[NP2];
 #pragma unroll
                 for (int k = 0; k < NP2; ++k) yp[k] = yv[k] = f2(0.f, 0.f);
 #pragma unroll SGPMP_T_UNROLL_C
@@ -166,17 +150,12 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                             ep[k] = f2(r0[(size_t)i0 * S], i1 < N ? r0[(size_t)i1 * S] : 0.f);
                             ev[k] = f2(r0[(size_t)(N + i0) * S], i1 < N ? r0[(size_t)(N + i1) * S] : 0.f);
                         }
-                    } else if ((t & 1) == 0) {
-#pragma unroll
-                        for (int k = 0; k < NP2; ++k) {
-                            float a0, a1, a2, a3, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-                            normal4<float>(key, t >> 1, 2 * k, A.sample_gid0 + (uint32_t)s0, pgid, a0, a1, a2, a3);
-                            if (2 * k + 1 < N) normal4<float>(key, t >> 1, 2 * k + 1, A.sample_gid0 + (uint32_t)s0, pgid, b0, b1, b2, b3);
-                            ep[k] = f2(a0, b0); ev[k] = f2(a1, b1); enp[k] = f2(a2, b2); env[k] = f2(a3, b3);
-                        }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < NP2; ++k) { ep[k] = enp[k]; ev[k] = env[k]; }
+                        for (int k = 0; k < NP2; ++k) {
+                            if (2 * k + 1 < N) normal_pair_f2<true>(key, (uint32_t)t, (uint32_t)k, A.sample_gid0 + (uint32_t)s0, pgid, ep[k], ev[k], dro);
+                            else normal_pair_f2<false>(key, (uint32_t)t, (uint32_t)k, A.sample_gid0 + (uint32_t)s0, pgid, ep[k], ev[k], dro);
+                        }
                     }
                     real r[8];
                     load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
@@ -217,31 +196,32 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 for (int i = 0; i < N; ++i) { yp[i] = vbroadcast<V>((real)0); yv[i] = vbroadcast<V>((real)0); }
                 // One Philox call per DoF (and lane) yields the normals of TWO time steps; the step body is kept as a
                 // single (not 2x unrolled) copy so that the hot loop stays inside the instruction cache.
-                V en[d];
     #pragma unroll 1
                 for (int t = 0; t < T; ++t) {
-                    V e[d];
+                    V e[d + 1];
                     if (eps) {
     #pragma unroll
                         for (int j = 0; j < d; ++j) {
                             const real* row = eps + ((size_t)t * d + j) * S;
                             if constexpr (W == 2) e[j] = f2(row[s0], row[s1]); else e[j] = row[s0];
                         }
-                    } else if ((t & 1) == 0) {
-    #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            if constexpr (W == 2) {
-                                float a0, a1, a2, a3, b0, b1, b2, b3;
-                                normal4<float>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s0, pgid, a0, a1, a2, a3);
-                                normal4<float>(key, t >> 1, i, A.sample_gid0 + (uint32_t)(s0 + 1), pgid, b0, b1, b2, b3);
-                                e[i] = f2(a0, b0); e[N + i] = f2(a1, b1); en[i] = f2(a2, b2); en[N + i] = f2(a3, b3);
-                            } else {
-                                normal4<real>(key, t >> 1, i, A.sample_gid0 + (uint32_t)s0, pgid, e[i], e[N + i], en[i], en[N + i]);
-                            }
-                        }
                     } else {
     #pragma unroll
-                        for (int j = 0; j < d; ++j) e[j] = en[j];
+                        for (int k = 0; k < (N + 1) / 2; ++k) {
+                            constexpr int NN = N;
+                            const bool full = (2 * k + 1 < NN);
+                            if constexpr (W == 2) {
+                                float a0, a1, a2, a3, b0, b1, b2, b3;
+                                normal_pair<float>(key, (uint32_t)t, (uint32_t)k, full, A.sample_gid0 + (uint32_t)s0, pgid, a0, a1, a2, a3, dro);
+                                normal_pair<float>(key, (uint32_t)t, (uint32_t)k, full, A.sample_gid0 + (uint32_t)(s0 + 1), pgid, b0, b1, b2, b3, dro);
+                                e[2 * k] = f2(a0, b0); e[N + 2 * k] = f2(a2, b2);
+                                if (full) { e[2 * k + 1] = f2(a1, b1); e[N + 2 * k + 1] = f2(a3, b3); }
+                            } else {
+                                real p1, v1;
+                                normal_pair<real>(key, (uint32_t)t, (uint32_t)k, full, A.sample_gid0 + (uint32_t)s0, pgid, e[2 * k], p1, e[N + 2 * k], v1, dro);
+                                if (full) { e[2 * k + 1] = p1; e[N + 2 * k + 1] = v1; }
+                            }
+                        }
                     }
                     real r[8], m[DP];
                     load4(tabGH + t * 8, r[0], r[1], r[2], r[3]);
@@ -335,21 +315,23 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 if (lane == 0) acc[r] = a;
             }
         } else {
-            const int n_items = TP * N;
+            constexpr int NPAIR = (N + 1) / 2;
+            const int n_items = T * NPAIR;                    // one item = the 4 normals of (time step, DoF pair)
             const int nsplit = (n_items < BS) ? (BS / n_items) : 1;
             for (int base = 0; base < n_items; base += BS) {
                 const int item = base + (tid % (nsplit > 1 ? n_items : BS));
                 const int split = (nsplit > 1) ? tid / n_items : 0;
                 const bool active = item < n_items && split < nsplit;
                 real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                const int tp = item / N, i = item - tp * N;
+                const int t_ = item / NPAIR, k = item - t_ * NPAIR;
+                const bool full = (2 * k + 1 < N);
                 if (active) {
                     for (int s = split; s < ns; s += nsplit) {
                         const real w = wsm[s];
                         if (w == (real)0) continue;
-                        real p0, v0, p1, v1;
-                        normal4<real>(key, tp, i, A.sample_gid0 + (uint32_t)(s_lo + s), pgid, p0, v0, p1, v1);
-                        a0 += w * p0; a1 += w * v0; a2 += w * p1; a3 += w * v1;
+                        real p0, p1, v0, v1;
+                        normal_pair<real>(key, (uint32_t)t_, (uint32_t)k, full, A.sample_gid0 + (uint32_t)(s_lo + s), pgid, p0, p1, v0, v1, dro);
+                        a0 += w * p0; a1 += w * p1; a2 += w * v0; a3 += w * v1;
                     }
                 }
                 if (nsplit > 1) {
@@ -363,12 +345,11 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                     }
                 }
                 if (active && split == 0) {
-                    const int t0 = 2 * tp;
-                    acc[t0 * d + i] = a0;
-                    acc[t0 * d + N + i] = a1;
-                    if (t0 + 1 < T) {
-                        acc[(t0 + 1) * d + i] = a2;
-                        acc[(t0 + 1) * d + N + i] = a3;
+                    acc[t_ * d + 2 * k] = a0;
+                    acc[t_ * d + N + 2 * k] = a2;
+                    if (full) {
+                        acc[t_ * d + 2 * k + 1] = a1;
+                        acc[t_ * d + N + 2 * k + 1] = a3;
                     }
                 }
             }
@@ -446,20 +427,24 @@ static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P,
     return SGPMP_OK;
 }
 
+// few problems: split every particle's samples over a cluster of 8 / 4 / 2 CTAs (DSMEM reductions) so that the
+// launch still covers the 148 SMs: the largest cluster that keeps <= 2 CTAs per SM and >= 64 samples per CTA
+static int iterate_cluster_size(const sgpmp_shape_t& sh, bool injected_eps) {
+    static const char* cl_env = getenv("SGPMP_ITERATE_CLUSTER");    // 0 disables
+    const long n_part = (long)sh.B * sh.G * sh.K;
+    if ((cl_env && atoi(cl_env) == 0) || injected_eps) return 1;
+    for (int c = 8; c >= 2; c >>= 1)
+        if (n_part * c <= 2 * 148 && sh.S >= 64 * c && (c == 8 ? sh.S >= 256 : true)) return c;
+    return 1;
+}
+
 template <typename real, int N, int CHAIN>
 static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const IterArgs<real>& A, cudaStream_t st) {
     static const char* force_bs = getenv("SGPMP_ITERATE_BS");       // tuning aids
     static const char* pack_env = getenv("SGPMP_ITERATE_PACK");     // 0 scalar, 2 dof pairs (default)
     const bool bs128 = force_bs && atoi(force_bs) == 128;
-    // few problems: split every particle's samples over a cluster of 8 / 4 / 2 CTAs (DSMEM reductions) so that the
-    // launch still covers the 148 SMs: the largest cluster that keeps <= 2 CTAs per SM and >= 64 samples per CTA
-    static const char* cl_env = getenv("SGPMP_ITERATE_CLUSTER");    // 0 disables
     const long n_part = (long)sh.B * sh.G * sh.K;
-    int cl = 1;
-    if (!(cl_env && atoi(cl_env) == 0) && !A.eps_in) {
-        for (int c = 8; c >= 2; c >>= 1)
-            if (n_part * c <= 2 * 148 && sh.S >= 64 * c && (c == 8 ? sh.S >= 256 : true)) { cl = c; break; }
-    }
+    const int cl = iterate_cluster_size(sh, A.eps_in != nullptr);
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const bool pairs_ok_c = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (pairs_ok_c) {
@@ -508,14 +493,21 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     A.particle_gid0 = (uint32_t)(sh.problem_gid0 * sh.G * sh.K);
     A.sample_gid0 = (uint32_t)sh.sample_gid0;
     A.step = (real)step;
-    A.key = RngKey{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw0};
+    A.key = make_rng_key(seed, draw0);
     A.tab = tables;
     A.eps_in = (const real*)eps_in;
     A.means = (real*)means; A.means_pre = (real*)means_pre; A.samples = (real*)samples;
     A.costs = (real*)costs; A.weights = (real*)weights; A.grad = (real*)grad;
     if constexpr (sizeof(real) == 4) {
-        if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof))
+        if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof)) {
+            // Panda structure: role-split kernel (sgpmp_iterate_split.cu) unless the grid is small enough for cluster mode
+            static const char* split_env = getenv("SGPMP_ITERATE_SPLIT");     // 0 selects the single-role kernel
+            if (!(split_env && atoi(split_env) == 0) && iterate_cluster_size(sh, A.eps_in != nullptr) == 1) {
+                rc = launch_iterate_split(sh, P, A, P.has_self ? 2 : 1, st);
+                if (rc != SGPMP_ERR_UNSUPPORTED) return rc;
+            }
             return P.has_self ? launch_iterate_n<real, 7, 2>(sh, P, A, st) : launch_iterate_n<real, 7, 1>(sh, P, A, st);
+        }
     }
     switch (sh.n_dof) {
 #define SGPMP_DOF_CASE(N) case N: return launch_iterate_n<real, N, 0>(sh, P, A, st);

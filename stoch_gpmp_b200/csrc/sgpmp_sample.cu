@@ -5,8 +5,9 @@
 // loc + L @ eps with a dense M x M L per particle (2 NP S M^2 flop, 84-91 % of the reference's
 // iteration).  L^-1 is block-bidiagonal, so  y_t = G_t eps_t - H_t y_{t-1}  (16 flop per state).
 //
-// Mapping: one thread per (sample, DoF); the S-minor layout [B,NP,T,d,S] makes every load/store of a
-// warp one contiguous 128-byte (fp32) line.  The G/H tables (7 reals per step) sit in shared memory.
+// Mapping: one thread per (sample, DoF pair) — the unit of the RNG stream (sgpmp_rng.cuh); the S-minor layout
+// [B,NP,T,d,S] makes every load/store of a warp one contiguous 128-byte (fp32) line.  The G/H tables (7 reals per
+// step) sit in shared memory.
 #include "sgpmp_common.cuh"
 #include "sgpmp_rng.cuh"
 
@@ -31,98 +32,98 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sampl
         for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu_s[k] = means[(size_t)bp * T * d + k];
     __syncthreads();
 
+    const int n_pairs = (n + 1) >> 1;
     const int idx = blockIdx.y * blockDim.x + threadIdx.x;
-    if (idx >= S * n) return;
-    const int i = idx / S, s = idx - i * S;
+    if (idx >= S * n_pairs) return;
+    const int k = idx / S, s = idx - k * S;
+    const int i0 = 2 * k;
+    const bool full = (i0 + 1 < n);
     const size_t base = (size_t)bp * T * d * S;      // samples / eps
     const real* mu = mu_in_smem ? mu_s : means + (size_t)bp * T * d;
     const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
 
-    real yp = 0, yv = 0;
-    for (int tp = 0; tp < (T + 1) / 2; ++tp) {
-        real e[4];
+    real yp[2] = {0, 0}, yv[2] = {0, 0};
+    for (int t = 0; t < T; ++t) {
+        real ep[2] = {0, 0}, ev[2] = {0, 0};
         if (eps_in) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = 2 * tp + h;
-                if (t < T) {
-                    e[2 * h] = eps_in[base + ((size_t)t * d + i) * S + s];
-                    e[2 * h + 1] = eps_in[base + ((size_t)t * d + n + i) * S + s];
-                } else {
-                    e[2 * h] = e[2 * h + 1] = 0;
+            for (int h = 0; h < 2; ++h)
+                if (h == 0 || full) {
+                    ep[h] = eps_in[base + ((size_t)t * d + i0 + h) * S + s];
+                    ev[h] = eps_in[base + ((size_t)t * d + n + i0 + h) * S + s];
                 }
-            }
         } else {
-            normal4<real>(key, tp, i, sample_gid0 + (uint32_t)s, pgid, e[0], e[1], e[2], e[3]);
+            normal_pair<real>(key, (uint32_t)t, (uint32_t)k, full, sample_gid0 + (uint32_t)s, pgid, ep[0], ep[1], ev[0], ev[1]);
         }
+        const real* r = gh + t * 7;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int t = 2 * tp + h;
-            if (t < T) {
-                const real* r = gh + t * 7;
-                const real np_ = r[0] * e[2 * h] - (r[3] * yp + r[4] * yv);
-                const real nv_ = r[1] * e[2 * h] + r[2] * e[2 * h + 1] - (r[5] * yp + r[6] * yv);
-                yp = np_; yv = nv_;
-                const size_t op = base + ((size_t)t * d + i) * S + s;
-                const size_t ov = base + ((size_t)t * d + n + i) * S + s;
-                samples[op] = mu[t * d + i] + yp;
-                samples[ov] = mu[t * d + n + i] + yv;
-                if (eps_out) { eps_out[op] = e[2 * h]; eps_out[ov] = e[2 * h + 1]; }
+        for (int h = 0; h < 2; ++h)
+            if (h == 0 || full) {
+                const real np_ = r[0] * ep[h] - (r[3] * yp[h] + r[4] * yv[h]);
+                const real nv_ = r[1] * ep[h] + r[2] * ev[h] - (r[5] * yp[h] + r[6] * yv[h]);
+                yp[h] = np_; yv[h] = nv_;
+                const size_t op = base + ((size_t)t * d + i0 + h) * S + s;
+                const size_t ov = base + ((size_t)t * d + n + i0 + h) * S + s;
+                samples[op] = mu[t * d + i0 + h] + np_;
+                samples[ov] = mu[t * d + n + i0 + h] + nv_;
+                if (eps_out) { eps_out[op] = ep[h]; eps_out[ov] = ev[h]; }
             }
-        }
     }
 }
 
-// Few-samples variant (one planning problem): one CTA per (particle, DoF, block of 128 samples).  The normals of all T steps are
-// drawn first, by all 256 threads in parallel over (time pair, sample) — the counter-based stream does not care who draws — into
-// shared memory; only then does one thread per sample walk the (cheap) recurrence.  In sample_kernel a thread draws AND walks, i.e.
-// 32 dependent Philox / Box-Muller chains back to back: with 2,048 samples that is a few lone warps (20 us at B = 1).
-// Same stream, same recurrence expressions: bit-identical output.
+// Few-samples variant (one planning problem): one CTA per (particle, DoF pair, block of 64 samples).  The normals of all T steps
+// are drawn first, by all 256 threads in parallel over (time step, sample) — the counter-based stream does not care who draws —
+// into shared memory; only then does one thread per (sample, DoF of the pair) walk the (cheap) recurrence.  In sample_kernel a
+// thread draws AND walks, i.e. T dependent Philox / Box-Muller chains back to back: with 2,048 samples that is a few lone warps
+// (20 us at B = 1).  Same stream, same recurrence expressions: bit-identical output.
+constexpr int SAMPLE_TILE_SB = 64;
 template <typename real>
 __global__ void __launch_bounds__(256)
 sample_tiled_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
                     const real* __restrict__ means, RngKey key, real* __restrict__ samples) {
-    constexpr int SB = 128;
+    constexpr int SB = SAMPLE_TILE_SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int TP = (T + 1) / 2;
     real* gh = reinterpret_cast<real*>(smem_raw);       // [T][7]
-    real* mu_i = gh + (size_t)T * 7;                    // [T][2]  (pos, vel) mean of this DoF
-    real* eps = mu_i + (size_t)T * 2;                   // [2 TP][2][SB]
-    const int bp = blockIdx.x, i = blockIdx.y, s0 = blockIdx.z * SB;
-    const int d = 2 * n;
-    for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
-        gh[k] = (real)tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + (k % 7)];
-    for (int k = threadIdx.x; k < T * 2; k += blockDim.x)
-        mu_i[k] = means[(size_t)bp * T * d + (size_t)(k >> 1) * d + (k & 1) * n + i];
+    real* mu_k = gh + (size_t)T * 7;                    // [T][4]  (pos 2k, pos 2k+1, vel 2k, vel 2k+1) mean of this pair
+    real* eps = mu_k + (size_t)T * 4;                   // [T][4][SB]  same component order
+    const int bp = blockIdx.x, k = blockIdx.y, s0 = blockIdx.z * SB;
+    const int d = 2 * n, i0 = 2 * k;
+    const bool full = (i0 + 1 < n);
+    for (int q = threadIdx.x; q < T * 7; q += blockDim.x)
+        gh[q] = (real)tab[(size_t)(q / 7) * SGPMP_TABLE_STRIDE + (q % 7)];
+    for (int q = threadIdx.x; q < T * 4; q += blockDim.x) {
+        const int t = q >> 2, c = q & 3, h = c & 1, a = c >> 1;
+        mu_k[q] = (h == 0 || full) ? means[(size_t)bp * T * d + (size_t)t * d + a * n + i0 + h] : (real)0;
+    }
     const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
-    for (int item = threadIdx.x; item < TP * SB; item += blockDim.x) {
-        const int tp = item / SB, sl = item - tp * SB, s = s0 + sl;
+    for (int item = threadIdx.x; item < T * SB; item += blockDim.x) {
+        const int t = item / SB, sl = item - t * SB, s = s0 + sl;
         if (s < S) {
-            real e0, e1, e2, e3;
-            normal4<real>(key, tp, i, sample_gid0 + (uint32_t)s, pgid, e0, e1, e2, e3);
-            real* e = eps + (size_t)(2 * tp) * 2 * SB + sl;
-            e[0] = e0; e[SB] = e1; e[2 * SB] = e2; e[3 * SB] = e3;
+            real p0, p1, v0, v1;
+            normal_pair<real>(key, (uint32_t)t, (uint32_t)k, full, sample_gid0 + (uint32_t)s, pgid, p0, p1, v0, v1);
+            real* e = eps + (size_t)t * 4 * SB + sl;
+            e[0] = p0; e[SB] = p1; e[2 * SB] = v0; e[3 * SB] = v1;
         }
     }
     __syncthreads();
-    const int sl = threadIdx.x, s = s0 + sl;
-    if (sl >= SB || s >= S) return;
+    const int h = threadIdx.x / SB, sl = threadIdx.x - h * SB, s = s0 + sl;
+    if (h >= 2 || s >= S || (h == 1 && !full)) return;
     const size_t base = (size_t)bp * T * d * S;
     real yp = 0, yv = 0;
     for (int t = 0; t < T; ++t) {
         const real* r = gh + t * 7;
-        const real e0 = eps[(size_t)t * 2 * SB + sl], e1 = eps[(size_t)t * 2 * SB + SB + sl];
+        const real e0 = eps[((size_t)t * 4 + h) * SB + sl], e1 = eps[((size_t)t * 4 + 2 + h) * SB + sl];
         const real np_ = r[0] * e0 - (r[3] * yp + r[4] * yv);
         const real nv_ = r[1] * e0 + r[2] * e1 - (r[5] * yp + r[6] * yv);
         yp = np_; yv = nv_;
-        samples[base + ((size_t)t * d + i) * S + s] = mu_i[2 * t] + yp;
-        samples[base + ((size_t)t * d + n + i) * S + s] = mu_i[2 * t + 1] + yv;
+        samples[base + ((size_t)t * d + i0 + h) * S + s] = mu_k[4 * t + h] + np_;
+        samples[base + ((size_t)t * d + n + i0 + h) * S + s] = mu_k[4 * t + 2 + h] + nv_;
     }
 }
 
 // In-kernel-RNG variant for the instantiated DoF counts: one thread per SAMPLE with all DoFs in registers (the
 // mapping of the fused kernel's pass 1).  The generic kernel above spends 44 k instructions per trajectory sample
-// (per-thread index arithmetic for one DoF); this one ~23 k, which moves the kernel from 35 % to >60 % of the HBM
+// (per-thread index arithmetic for one DoF pair); this one ~23 k, which moves the kernel from 35 % to >60 % of the HBM
 // write roofline.  Row (t, j) of the S-minor output is written by consecutive threads: fully coalesced.
 template <typename real, int N>
 __global__ void __launch_bounds__(128)
@@ -141,18 +142,17 @@ sample_rng_kernel(int S, int T, int64_t particle_gid0, uint32_t sample_gid0, con
     const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
     real* out = samples + (size_t)bp * T * d * S + s;
     real* eo = eps_out ? eps_out + (size_t)bp * T * d * S + s : nullptr;
-    real yp[N], yv[N], en[d];
+    real yp[N], yv[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { yp[i] = 0; yv[i] = 0; }
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-        real e[d];
-        if ((t & 1) == 0) {
+        real e[d + 2];
 #pragma unroll
-            for (int i = 0; i < N; ++i) normal4<real>(key, t >> 1, i, sample_gid0 + (uint32_t)s, pgid, e[i], e[N + i], en[i], en[N + i]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < d; ++j) e[j] = en[j];
+        for (int k = 0; k < (N + 1) / 2; ++k) {
+            real p1, v1;
+            normal_pair<real>(key, (uint32_t)t, (uint32_t)k, 2 * k + 1 < N, sample_gid0 + (uint32_t)s, pgid, e[2 * k], p1, e[N + 2 * k], v1);
+            if (2 * k + 1 < N) { e[2 * k + 1] = p1; e[N + 2 * k + 1] = v1; }
         }
         const real* r = gh + t * 8;
         const real* m = mu + t * d;
@@ -183,7 +183,7 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
         if (smem > 227 * 1024) return SGPMP_ERR_UNSUPPORTED;      // caller falls back to the generic kernel
         cudaFuncSetAttribute(sample_rng_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
+    RngKey key = make_rng_key(seed, draw);
     sample_rng_kernel<real, N><<<grid, bs, smem, st>>>(sh.S, sh.T, sh.problem_gid0 * NP, (uint32_t)sh.sample_gid0, tables,
                                                        (const real*)means, key, (real*)samples, (real*)eps_out);
     SGPMP_CHECK_LAUNCH("sgpmp_sample");
@@ -194,13 +194,14 @@ template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
                          uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false) {
     if (few && !eps_in && !eps_out) {
-        const int TP = (sh.T + 1) / 2;
-        const size_t smem = ((size_t)sh.T * 9 + (size_t)2 * TP * 2 * 128) * sizeof(real);
-        if (smem <= 200 * 1024 && sh.n_dof <= 65535 && (sh.S + 127) / 128 <= 65535) {
+        constexpr int SB = SAMPLE_TILE_SB;
+        const int n_pairs = (sh.n_dof + 1) / 2;
+        const size_t smem = ((size_t)sh.T * 11 + (size_t)sh.T * 4 * SB) * sizeof(real);
+        if (smem <= 200 * 1024 && n_pairs <= 65535 && (sh.S + SB - 1) / SB <= 65535) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             const int NPf = sh.G * sh.K;
-            RngKey keyf{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
-            sample_tiled_kernel<real><<<dim3((unsigned)(sh.B * NPf), (unsigned)sh.n_dof, (unsigned)((sh.S + 127) / 128)), 256, smem, st>>>(
+            RngKey keyf = make_rng_key(seed, draw);
+            sample_tiled_kernel<real><<<dim3((unsigned)(sh.B * NPf), (unsigned)n_pairs, (unsigned)((sh.S + SB - 1) / SB)), 256, smem, st>>>(
                 NPf, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NPf, (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples);
             SGPMP_CHECK_LAUNCH("sgpmp_sample(tiled)");
             return SGPMP_OK;
@@ -223,7 +224,7 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
     }
     const int NP = sh.G * sh.K;
     const int bs = 256;
-    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S * sh.n_dof + bs - 1) / bs));
+    dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S * ((sh.n_dof + 1) / 2) + bs - 1) / bs));
     size_t smem = (size_t)sh.T * 7 * sizeof(real);
     const size_t mu_bytes = (size_t)sh.T * 2 * sh.n_dof * sizeof(real);
     const int mu_in_smem = (smem + mu_bytes <= 40 * 1024) ? 1 : 0;
@@ -232,7 +233,7 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
         if (smem > 227 * 1024) { set_error("sgpmp_sample: T=%d too large for the shared-memory tables", sh.T); return SGPMP_ERR_UNSUPPORTED; }
         cudaFuncSetAttribute(sample_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), draw};
+    RngKey key = make_rng_key(seed, draw);
     sample_kernel<real><<<grid, bs, smem, st>>>(NP, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NP, (uint32_t)sh.sample_gid0, tables,
                                                 (const real*)means, (const real*)eps_in, key, (real*)samples,
                                                 (real*)eps_out, mu_in_smem);

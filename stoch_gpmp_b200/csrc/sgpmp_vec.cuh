@@ -67,39 +67,47 @@ __device__ __forceinline__ float vexp2_fast(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ double vexp2_fast(double x) { return exp(x); }
 __device__ __forceinline__ F2 vexp2_fast(F2 x) { return f2(vexp2_fast(lane0(x)), vexp2_fast(lane1(x))); }
 
-// sin/cos of joint angles.  fp32: branch-free Cody-Waite + cephes minimax polynomials on the FMA pipe (max abs
-// error 7e-8 on |x| <= 12; libdevice sincosf costs ~28 issue slots incl. a divergent slow-path guard, this ~21,
-// and the packed form ~13 per angle).  fp64: libdevice.
+// sin/cos of joint angles.  fp32: branch-free on the FMA pipe — x = j pi + r with j = rint(x / pi) (magic-number rounding,
+// two-term Cody-Waite), sin x = (-1)^j sin r, cos x = (-1)^j cos r, minimax polynomials on |r| <= pi/2 (max abs error
+// 1.2e-7 on |x| <= 4.5, the fp32 rounding floor of values near 1).  Reducing by pi instead of pi/2 costs two more
+// polynomial terms but removes the quadrant swap: the sign is ONE xor per output with the parity bit of the magic
+// sum.  Packed form: 16 FFMA2/FMUL2/FADD2 + 6 integer ops per angle PAIR.  fp64: libdevice.
 __device__ __forceinline__ void vsincos(double x, double* s, double* c) { sincos(x, s, c); }
+#define SGPMP_SIN_C0 -0.1666666716337204f
+#define SGPMP_SIN_C1 0.008333331905305386f
+#define SGPMP_SIN_C2 -0.00019840880122501403f
+#define SGPMP_SIN_C3 2.7522235086507862e-06f
+#define SGPMP_SIN_C4 -2.377893792981922e-08f
+#define SGPMP_COS_C0 -0.5f
+#define SGPMP_COS_C1 0.0416666604578495f
+#define SGPMP_COS_C2 -0.0013888651737943292f
+#define SGPMP_COS_C3 2.477461748640053e-05f
+#define SGPMP_COS_C4 -2.629822404287552e-07f
 __device__ __forceinline__ void vsincos(float x, float* sp, float* cp) {
-    const float t = fmaf(x, 0.636619772367581f, 12582912.0f);   // 1.5 * 2^23: rint(x * 2/pi) lands in the low mantissa bits
-    const int q = __float_as_int(t);
+    const float t = fmaf(x, 0.3183098861837907f, 12582912.0f);   // 1.5 * 2^23: rint(x / pi) lands in the low mantissa bits
+    const unsigned sb = __float_as_uint(t) << 31;
     const float j = t - 12582912.0f;
-    float r = fmaf(j, -1.5707963705062866f, x);        // pi/2 = C1 + C2 (+ 1.7e-15)
-    r = fmaf(j, 4.371138828673793e-08f, r);
+    float r = fmaf(j, -3.1415927410125732f, x);        // pi = C1 + C2
+    r = fmaf(j, 8.742277657347586e-08f, r);
     const float z = r * r;
-    const float s = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
-    const float c = fmaf(fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z, -0.5f), z, 1.0f);
-    const float ss = (q & 1) ? c : s;
-    const float cc = (q & 1) ? s : c;
-    *sp = __int_as_float(__float_as_int(ss) ^ ((q << 30) & 0x80000000));
-    *cp = __int_as_float(__float_as_int(cc) ^ (((q + 1) << 30) & 0x80000000));
+    const float ps = fmaf(fmaf(fmaf(fmaf(SGPMP_SIN_C4, z, SGPMP_SIN_C3), z, SGPMP_SIN_C2), z, SGPMP_SIN_C1), z, SGPMP_SIN_C0) * z;
+    const float s = fmaf(ps, r, r);
+    const float c = fmaf(fmaf(fmaf(fmaf(fmaf(SGPMP_COS_C4, z, SGPMP_COS_C3), z, SGPMP_COS_C2), z, SGPMP_COS_C1), z, SGPMP_COS_C0), z, 1.0f);
+    *sp = __uint_as_float(__float_as_uint(s) ^ sb);
+    *cp = __uint_as_float(__float_as_uint(c) ^ sb);
 }
 __device__ __forceinline__ void vsincos(F2 x, F2* sp, F2* cp) {
-    const F2 t = vfma(x, 0.636619772367581f, 12582912.0f);
-    const int q0 = __float_as_int(lane0(t)), q1 = __float_as_int(lane1(t));
+    const F2 t = vfma(x, 0.3183098861837907f, 12582912.0f);
+    const unsigned sb0 = __float_as_uint(lane0(t)) << 31, sb1 = __float_as_uint(lane1(t)) << 31;
     const F2 j = t - 12582912.0f;
-    F2 r = vfma(j, -1.5707963705062866f, x);
-    r = vfma(j, 4.371138828673793e-08f, r);
+    F2 r = vfma(j, -3.1415927410125732f, x);
+    r = vfma(j, 8.742277657347586e-08f, r);
     const F2 z = r * r;
-    const F2 ps = vfma(vfma(f2(-1.9515295891e-4f, -1.9515295891e-4f), z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z;
+    const F2 ps = vfma(vfma(vfma(vfma(f2(SGPMP_SIN_C4, SGPMP_SIN_C4), z, SGPMP_SIN_C3), z, SGPMP_SIN_C2), z, SGPMP_SIN_C1), z, SGPMP_SIN_C0) * z;
     const F2 s = vfma(ps, r, r);
-    const F2 c = vfma(vfma(vfma(vfma(f2(2.443315711809948e-5f, 2.443315711809948e-5f), z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z, -0.5f), z, 1.0f);
-    const float s0 = lane0(s), s1 = lane1(s), c0 = lane0(c), c1 = lane1(c);
-    const float ss0 = (q0 & 1) ? c0 : s0, cc0 = (q0 & 1) ? s0 : c0;
-    const float ss1 = (q1 & 1) ? c1 : s1, cc1 = (q1 & 1) ? s1 : c1;
-    *sp = f2(__int_as_float(__float_as_int(ss0) ^ ((q0 << 30) & 0x80000000)), __int_as_float(__float_as_int(ss1) ^ ((q1 << 30) & 0x80000000)));
-    *cp = f2(__int_as_float(__float_as_int(cc0) ^ (((q0 + 1) << 30) & 0x80000000)), __int_as_float(__float_as_int(cc1) ^ (((q1 + 1) << 30) & 0x80000000)));
+    const F2 c = vfma(vfma(vfma(vfma(vfma(f2(SGPMP_COS_C4, SGPMP_COS_C4), z, SGPMP_COS_C3), z, SGPMP_COS_C2), z, SGPMP_COS_C1), z, SGPMP_COS_C0), z, 1.0f);
+    *sp = f2(__uint_as_float(__float_as_uint(lane0(s)) ^ sb0), __uint_as_float(__float_as_uint(lane1(s)) ^ sb1));
+    *cp = f2(__uint_as_float(__float_as_uint(lane0(c)) ^ sb0), __uint_as_float(__float_as_uint(lane1(c)) ^ sb1));
 }
 
 }  // namespace sgpmp

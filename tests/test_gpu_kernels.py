@@ -766,7 +766,7 @@ def test_lowlat_iteration_equals_separate_kernels(name, cuda):
         out = _ops().iterate(sh, desc, tab, spec['step_size'], 1, mu_l, seed=11, draw0=it, want_samples=True, lowlat=True)
         assert torch.equal(out['means_pre'], mu)
         assert torch.equal(out['samples'], xs)
-        assert float((out['costs'] - c).abs().max() / c.abs().max()) < (2e-6 if f32 else 1e-13)
+        assert float((out['costs'] - c).abs().max() / c.abs().max()) < (4e-6 if f32 else 1e-13)    # two summation orders of the same terms
         mu_k = mu.clone()
         grad, w = _ops().update(sh, spec['temperature'], spec['step_size'], out['costs'], xs, mu_k)
         assert torch.equal(out['weights'], w)
