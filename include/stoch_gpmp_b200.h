@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGPMP_ABI_VERSION 5
+#define SGPMP_ABI_VERSION 6
 
 enum { SGPMP_F32 = 0, SGPMP_F64 = 1 };
 
@@ -244,6 +244,35 @@ int sgpmp_local_stats(const sgpmp_shape_t* shape, double temperature, const void
                       void* stats, void* stream);
 int sgpmp_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size,
                       const void* stats, void* means, void* grad, void* stream);
+
+/* Split-particle mode without materialised samples (round 2).  The arithmetic being split is the reference's
+ * _update_distribution, stoch_gpmp/planner.py:263-275 (softmax over ALL S samples of a particle, weighted mean update).
+ *
+ * sgpmp_iterate_stats: ONE fused launch over the samples [shape->sample_gid0, + shape->S) of every particle: sample -> cost
+ *   -> local softmax statistics  stats[B,NP, 2 + M] = (m, Z, A)  (definitions above); `means` are read only, `costs`
+ *   [B,NP,S] is optional.  The weighted eps-sum is regenerated from the counter-based RNG stream, nothing is materialised.
+ * sgpmp_merge_apply_stats: stats_all [n_ranks][B,NP, 2 + M] are merged by log-sum-exp in rank order inside the kernel
+ *   (m = max_r m_r, Z = sum_r Z_r e^(m_r - m), A = sum_r A_r e^(m_r - m)) and mu += step L (A/Z) is applied; grad optional.
+ * sgpmp_comm_*: an NCCL communicator owned by this library (libnccl is resolved with dlopen at run time; sgpmp_nccl_load
+ *   may name its path first).  Rank 0 calls sgpmp_comm_unique_id, the 128 bytes travel to the other ranks by any means
+ *   (the Python host uses torch.distributed), every rank calls sgpmp_comm_init.
+ * sgpmp_allreduce_stats: the exchange step — ncclAllGather of the local blocks into stats_all on `stream`.
+ * sgpmp_iterate_split_particles: n_iters iterations of  iterate_stats -> all_gather -> merge_apply  enqueued on `stream`
+ *   by one call (no host synchronisation; comm may be NULL iff n_ranks == 1).  means_pre (optional) receives the means
+ *   before the LAST update, costs (optional) this rank's costs and grad (optional) the gradient of the last iteration. */
+int sgpmp_iterate_stats(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+                        uint64_t seed, uint32_t draw, const void* means, void* costs, void* stats, void* stream);
+int sgpmp_merge_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size, const void* stats_all,
+                            int32_t n_ranks, void* means, void* grad, void* stream);
+int sgpmp_nccl_load(const char* path);
+int sgpmp_comm_unique_id(void* id128);
+int sgpmp_comm_init(const void* id128, int32_t rank, int32_t n_ranks, void** comm);
+int sgpmp_comm_destroy(void* comm);
+int sgpmp_allreduce_stats(void* comm, const sgpmp_shape_t* shape, const void* stats_local, void* stats_all, void* stream);
+int sgpmp_iterate_split_particles(const sgpmp_shape_t* shape_local, const sgpmp_cost_desc_t* desc, const double* tables,
+                                  double step_size, int32_t n_iters, uint64_t seed, uint32_t draw0, void* means,
+                                  void* means_pre, void* comm, int32_t n_ranks, void* stats_local, void* stats_all,
+                                  void* costs, void* grad, void* stream);
 
 /* Gauss-Newton GPMP (the reference's second planner, stoch_gpmp/planner.py:352-661): n_iters iterations of
  *   A, b, K = cost.get_linear_system(means)  (cost_functions.py:60-85);  J^T J = A^T K A + damping  (planner.py:602-617);

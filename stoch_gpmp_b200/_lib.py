@@ -4,6 +4,7 @@ There is deliberately no fallback: if the library is missing or a call fails, th
 """
 import ctypes as C
 import os
+import shutil
 
 from . import build as _build
 
@@ -18,7 +19,7 @@ MAX_INTERP = 8
 MAX_LINK_POINTS = 48
 NUM_TERMS = 7
 TERM_NAMES = ("start", "gp", "goal", "coll", "is", "self", "ee")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Shape(C.Structure):
@@ -69,6 +70,14 @@ SIGNATURES = {
     "sgpmp_iterate_lowlat": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_local_stats": (C.c_int, [_SP, _dbl, _vp, _vp, _vp, _vp]),
     "sgpmp_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    "sgpmp_iterate_stats": (C.c_int, [_SP, _DP, _vp, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "sgpmp_merge_apply_stats": (C.c_int, [_SP, _vp, _dbl, _vp, _i32, _vp, _vp, _vp]),
+    "sgpmp_nccl_load": (C.c_int, [C.c_char_p]),
+    "sgpmp_comm_unique_id": (C.c_int, [_vp]),
+    "sgpmp_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_void_p)]),
+    "sgpmp_comm_destroy": (C.c_int, [_vp]),
+    "sgpmp_allreduce_stats": (C.c_int, [_vp, _SP, _vp, _vp, _vp]),
+    "sgpmp_iterate_split_particles": (C.c_int, [_SP, _DP, _vp, _dbl, _i32, _u64, _u32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "sgpmp_gpmp_workspace_bytes": (_i64, [_SP, _i32]),
     "sgpmp_gpmp_step": (C.c_int, [_SP, _DP, _vp, _vp, _dbl, _i32, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "sgpmp_sample_dense_tc": (C.c_int, [_SP, _vp, _vp, _vp, _vp, _vp]),
@@ -98,6 +107,12 @@ def load():
         raise ImportError(
             "stoch_gpmp_b200: CUDA library %s is missing — build it with `python -m stoch_gpmp_b200.build` "
             "(needs nvcc; there is no CPU fallback)" % path)
+    if path == _build.LIB and os.path.isdir(_build.CSRC) and not _build.is_fresh():
+        # a library older than csrc/ would silently validate old kernels
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            _build.build()
+        else:
+            raise ImportError("stoch_gpmp_b200: %s is older than the sources under csrc/ and nvcc is not available to rebuild it" % path)
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the symbol is not exported

@@ -81,6 +81,11 @@ int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const
 int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
                   void* grad, void* weights, int row_chunks, cudaStream_t st);
 
+int iterate_stats_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, uint64_t seed,
+                         uint32_t draw, const void* means, void* costs, void* stats, cudaStream_t st);
+int merge_apply_stats_launch(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats_all, int n_ranks,
+                             void* means, void* grad, cudaStream_t st);
+
 inline bool shape_ok(const sgpmp_shape_t* s) {
     return s && s->B > 0 && s->G > 0 && s->K > 0 && s->S > 0 && s->T >= 2 && s->n_dof > 0 && s->n_dof <= 255 &&
            (s->dtype == SGPMP_F32 || s->dtype == SGPMP_F64);

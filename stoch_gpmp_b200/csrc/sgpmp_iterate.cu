@@ -297,10 +297,15 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
                 Z = 0;
                 for (int r = 0; r < CL; ++r) Z += *cluster.map_shared_rank(xch + 1, r);     // fixed rank order: identical on every CTA
             }
-            for (int s = tid; s < ns; s += BS) {
-                const real w = wsm[s] / Z;
-                wsm[s] = w;
-                if (last && A.weights) A.weights[(size_t)bp * S + s_lo + s] = w;
+            if (A.stats_out) {
+                // split-particle mode: the weights stay UNNORMALISED (exp(z - m) of this rank's samples); (m, Z) go out with A
+                if (tid == 0) { A.stats_out[(size_t)bp * (M + 2)] = m; A.stats_out[(size_t)bp * (M + 2) + 1] = Z; }
+            } else {
+                for (int s = tid; s < ns; s += BS) {
+                    const real w = wsm[s] / Z;
+                    wsm[s] = w;
+                    if (last && A.weights) A.weights[(size_t)bp * S + s_lo + s] = w;
+                }
             }
             __syncthreads();
         }
@@ -369,6 +374,10 @@ iterate_kernel(const __grid_constant__ CostParams<real> P, const __grid_constant
             __syncthreads();
         }
 
+        if (A.stats_out) {       // split-particle mode: hand A = sum_s exp(z_s - m) eps_s to the exchange, no update here
+            for (int k = tid; k < M; k += BS) A.stats_out[(size_t)bp * (M + 2) + 2 + k] = acc[k];
+            return;
+        }
         // ---- grad = L acc (banded recurrence, one thread per DoF); mu += step * grad --------------------
         if (tid < N) {
             const int i = tid;
@@ -444,7 +453,7 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
     static const char* pack_env = getenv("SGPMP_ITERATE_PACK");     // 0 scalar, 2 dof pairs (default)
     const bool bs128 = force_bs && atoi(force_bs) == 128;
     const long n_part = (long)sh.B * sh.G * sh.K;
-    const int cl = iterate_cluster_size(sh, A.eps_in != nullptr);
+    const int cl = A.stats_out ? 1 : iterate_cluster_size(sh, A.eps_in != nullptr);
     if constexpr (sizeof(real) == 4 && (N == 2 || N == 7)) {
         const bool pairs_ok_c = ((CHAIN >= 1) || !(P.has_spheres || P.has_self)) && !(P.has_spheres && P.sphere_mode != SGPMP_FIELD_RBF);
         if (pairs_ok_c) {
@@ -483,7 +492,7 @@ static int launch_iterate_n(const sgpmp_shape_t& sh, const CostParams<real>& P, 
 template <typename real>
 static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, double step,
                           int n_iters, const void* eps_in, uint64_t seed, uint32_t draw0, void* means, void* means_pre,
-                          void* samples, void* costs, void* weights, void* grad, cudaStream_t st) {
+                          void* samples, void* costs, void* weights, void* grad, cudaStream_t st, void* stats_out = nullptr) {
     CostParams<real> P;
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
@@ -498,11 +507,12 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     A.eps_in = (const real*)eps_in;
     A.means = (real*)means; A.means_pre = (real*)means_pre; A.samples = (real*)samples;
     A.costs = (real*)costs; A.weights = (real*)weights; A.grad = (real*)grad;
+    A.stats_out = (real*)stats_out;
     if constexpr (sizeof(real) == 4) {
         if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof)) {
             // Panda structure: role-split kernel (sgpmp_iterate_split.cu) unless the grid is small enough for cluster mode
             static const char* split_env = getenv("SGPMP_ITERATE_SPLIT");     // 0 selects the single-role kernel
-            if (!(split_env && atoi(split_env) == 0) && iterate_cluster_size(sh, A.eps_in != nullptr) == 1) {
+            if (!(split_env && atoi(split_env) == 0) && (A.stats_out || iterate_cluster_size(sh, A.eps_in != nullptr) == 1)) {
                 rc = launch_iterate_split(sh, P, A, P.has_self ? 2 : 1, st);
                 if (rc != SGPMP_ERR_UNSUPPORTED) return rc;
             }
@@ -519,9 +529,26 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
     }
 }
 
+int iterate_stats_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, uint64_t seed,
+                         uint32_t draw, const void* means, void* costs, void* stats, cudaStream_t st) {
+    // one pass of sample -> cost -> local softmax statistics over THIS launch's samples (sample_gid0 .. + S); means are read only
+    if (sh.dtype == SGPMP_F32)
+        return launch_iterate<float>(sh, desc, tables, 0.0, 1, nullptr, seed, draw, const_cast<void*>(means), nullptr, nullptr, costs,
+                                     nullptr, nullptr, st, stats);
+    return launch_iterate<double>(sh, desc, tables, 0.0, 1, nullptr, seed, draw, const_cast<void*>(means), nullptr, nullptr, costs,
+                                  nullptr, nullptr, st, stats);
+}
+
 }  // namespace sgpmp
 
 using namespace sgpmp;
+
+extern "C" int sgpmp_iterate_stats(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
+                                   uint64_t seed, uint32_t draw, const void* means, void* costs, void* stats, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_iterate_stats: invalid shape");
+    SGPMP_REQUIRE(desc && tables && means && stats, "sgpmp_iterate_stats: null pointer");
+    return iterate_stats_launch(*shape, *desc, tables, seed, draw, means, costs, stats, (cudaStream_t)stream);
+}
 
 extern "C" int sgpmp_iterate(const sgpmp_shape_t* shape, const sgpmp_cost_desc_t* desc, const double* tables,
                              double step_size, int32_t n_iters, const void* eps_in, uint64_t seed, uint32_t draw0,

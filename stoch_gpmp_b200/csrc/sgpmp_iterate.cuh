@@ -19,6 +19,7 @@ struct IterArgs {
     real* costs;           // optional, last iteration
     real* weights;         // optional, last iteration
     real* grad;            // optional, last iteration
+    real* stats_out;       // split-particle mode: [B*NP][M+2] = (m, Z, A) of this launch's samples; the update is skipped
 };
 
 // Role-split fused iteration for the Panda structure (fp32, 7 DoF, RBF link fields): sgpmp_iterate_split.cu.

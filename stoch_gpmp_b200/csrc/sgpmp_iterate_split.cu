@@ -393,6 +393,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
         __syncthreads();
 
         // ---- softmax over the S samples of this particle ------------------------------------------------
+        float smax, ssum;
         {
             float m = -INFINITY;
             for (int s = tid; s < ns; s += BS) {
@@ -417,12 +418,14 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
             __syncthreads();
             Z = 0;
             for (int k = 0; k < BS / 32; ++k) Z += red[k];
+            smax = m; ssum = Z;
             // weights, and per 32-sample chunk the number of non-zero ones (the shipped configurations are one-hot)
             for (int c = warp; c < NCH; c += BS / 32) {
                 const int s = c * 32 + lane;
                 float w = 0.f;
                 if (s < ns) {
-                    w = wsm[s] / Z;
+                    // split-particle mode (stats_out): the weights stay UNNORMALISED, (m, Z) go out with A
+                    w = A.stats_out ? wsm[s] : wsm[s] / Z;
                     wsm[s] = w;
                     if (last && A.weights) A.weights[(size_t)bp * S + s] = w;
                 }
@@ -477,6 +480,11 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
         }
         __syncthreads();
 
+        if (A.stats_out) {       // split-particle mode: hand (m, Z, A = sum_s exp(z_s - m) eps_s) to the exchange, no update here
+            if (tid == 0) { A.stats_out[(size_t)bp * (M + 2)] = smax; A.stats_out[(size_t)bp * (M + 2) + 1] = ssum; }
+            for (int k = tid; k < M; k += BS) A.stats_out[(size_t)bp * (M + 2) + 2 + k] = acc[k];
+            return;
+        }
         // ---- grad = L acc (banded recurrence, one thread per DoF); mu += step * grad --------------------
         if (tid < N) {
             const int i = tid;

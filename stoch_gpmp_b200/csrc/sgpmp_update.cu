@@ -128,20 +128,39 @@ local_stats_kernel(int S, int M, real tau, const real* __restrict__ costs, const
 }
 
 // mu += step * L (A / Z): one thread per (particle, DoF) runs the banded recurrence over t.
+// n_ranks > 1: `stats` holds the gathered blocks [n_ranks][n_particles][M + 2] of the split-particle exchange; they are merged
+// here by log-sum-exp in a fixed rank order (m = max_r m_r, Z = sum_r Z_r e^(m_r - m), A = sum_r A_r e^(m_r - m)) — every rank
+// computes the identical update, no host arithmetic in between.
 template <typename real>
 __global__ void apply_stats_kernel(int n_particles, int T, int n, const double* __restrict__ tab, real step,
-                                   const real* __restrict__ stats, real* __restrict__ means, real* __restrict__ grad) {
+                                   const real* __restrict__ stats, int n_ranks, real* __restrict__ means, real* __restrict__ grad) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_particles * n) return;
     const int bp = idx / n, i = idx - bp * n;
     const int d = 2 * n;
     const size_t M = (size_t)T * d;
+    const size_t rank_stride = (size_t)n_particles * (M + 2);
     const real* st = stats + (size_t)bp * (M + 2);
-    const real invZ = (real)1 / st[1];
+    real m = st[0];
+    for (int r = 1; r < n_ranks; ++r) m = sg_max(m, st[r * rank_stride]);
+    real Z = 0;
+    for (int r = 0; r < n_ranks; ++r) Z += st[r * rank_stride + 1] * sg_exp(st[r * rank_stride] - m);
+    const real invZ = (real)1 / Z;
     real yp = 0, yv = 0;
     for (int t = 0; t < T; ++t) {
         const double* r = tab + (size_t)t * SGPMP_TABLE_STRIDE;
-        const real ep = st[2 + t * d + i] * invZ, ev = st[2 + t * d + n + i] * invZ;
+        real ep = 0, ev = 0;
+        if (n_ranks == 1) {
+            ep = st[2 + t * d + i];
+            ev = st[2 + t * d + n + i];
+        } else {
+            for (int q = 0; q < n_ranks; ++q) {
+                const real sc = sg_exp(st[q * rank_stride] - m);
+                ep += st[q * rank_stride + 2 + t * d + i] * sc;
+                ev += st[q * rank_stride + 2 + t * d + n + i] * sc;
+            }
+        }
+        ep *= invZ; ev *= invZ;
         const real np_ = (real)r[SGPMP_TAB_G11] * ep - ((real)r[SGPMP_TAB_H11] * yp + (real)r[SGPMP_TAB_H12] * yv);
         const real nv_ = (real)r[SGPMP_TAB_G21] * ep + (real)r[SGPMP_TAB_G22] * ev -
                          ((real)r[SGPMP_TAB_H21] * yp + (real)r[SGPMP_TAB_H22] * yv);
@@ -180,11 +199,11 @@ static int launch_local_stats(const sgpmp_shape_t& sh, double tau, const void* c
 
 template <typename real>
 static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats, void* means,
-                              void* grad, cudaStream_t st) {
+                              void* grad, cudaStream_t st, int n_ranks = 1) {
     const int n_particles = sh.B * sh.G * sh.K;
-    const int total = n_particles * sh.n_dof, bs = 128;
+    const int total = n_particles * sh.n_dof, bs = 64;
     apply_stats_kernel<real><<<(total + bs - 1) / bs, bs, 0, st>>>(n_particles, sh.T, sh.n_dof, tables, (real)step,
-                                                                  (const real*)stats, (real*)means, (real*)grad);
+                                                                  (const real*)stats, n_ranks, (real*)means, (real*)grad);
     SGPMP_CHECK_LAUNCH("sgpmp_apply_stats");
     return SGPMP_OK;
 }
@@ -195,9 +214,22 @@ int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* 
     return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks);
 }
 
+int merge_apply_stats_launch(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats_all, int n_ranks,
+                             void* means, void* grad, cudaStream_t st) {
+    if (sh.dtype == SGPMP_F32) return launch_apply_stats<float>(sh, tables, step, stats_all, means, grad, st, n_ranks);
+    return launch_apply_stats<double>(sh, tables, step, stats_all, means, grad, st, n_ranks);
+}
+
 }  // namespace sgpmp
 
 using namespace sgpmp;
+
+extern "C" int sgpmp_merge_apply_stats(const sgpmp_shape_t* shape, const double* tables, double step_size, const void* stats_all,
+                                       int32_t n_ranks, void* means, void* grad, void* stream) {
+    SGPMP_REQUIRE(shape_ok(shape), "sgpmp_merge_apply_stats: invalid shape");
+    SGPMP_REQUIRE(tables && stats_all && means && n_ranks >= 1, "sgpmp_merge_apply_stats: invalid argument");
+    return merge_apply_stats_launch(*shape, tables, step_size, stats_all, n_ranks, means, grad, (cudaStream_t)stream);
+}
 
 extern "C" int sgpmp_update(const sgpmp_shape_t* shape, double temperature, double step_size, const void* costs,
                             const void* samples, void* means, void* grad, void* weights, void* stream) {

@@ -193,6 +193,59 @@ def apply_stats(shape, tables, step_size, stats, means):
     return grad
 
 
+def iterate_stats(shape, desc, tables, means, seed, draw, want_costs=False):
+    """Split-particle mode, one fused launch: sample -> cost -> local softmax statistics over the samples
+    [shape.sample_gid0, + shape.S) of every particle.  Returns (stats [B,NP,M+2] = (m, Z, A), costs [B,NP,S] or None)."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
+    _req(means, "means", None, (B, NP, T, d))
+    stats = torch.empty(B, NP, T * d + 2, dtype=means.dtype, device=means.device)
+    costs = torch.empty(B, NP, S, dtype=means.dtype, device=means.device) if want_costs else None
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_iterate_stats(C.byref(shape), C.byref(desc), _ptr(tables), int(seed) & (2 ** 64 - 1), int(draw),
+                                           _ptr(means), _ptr(costs), _ptr(stats), _stream()), "sgpmp_iterate_stats")
+    return stats, costs
+
+
+def merge_apply_stats(shape, tables, step_size, stats_all, means):
+    """stats_all [R,B,NP,M+2] (rank-major) -> in-kernel log-sum-exp merge -> mu += step * L (A/Z) in place; returns grad."""
+    lib = _lib.load()
+    B, NP, T, d = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof
+    if stats_all.dim() == 3:
+        stats_all = stats_all.unsqueeze(0)
+    R = stats_all.shape[0]
+    _req(stats_all, "stats_all", means.dtype, (R, B, NP, T * d + 2))
+    _req(means, "means", None, (B, NP, T, d))
+    grad = torch.empty_like(means)
+    with torch.cuda.device(means.device):
+        _lib.check(lib.sgpmp_merge_apply_stats(C.byref(shape), _ptr(tables), float(step_size), _ptr(stats_all), int(R), _ptr(means),
+                                               _ptr(grad), _stream()), "sgpmp_merge_apply_stats")
+    return grad
+
+
+def iterate_split_particles(shape_local, desc, tables, step_size, n_iters, means, seed, draw0, comm=None, n_ranks=1,
+                            want_costs=True, want_grad=True, want_means_pre=True):
+    """n_iters split-particle iterations enqueued by ONE C call: per iteration a fused stats launch over this rank's samples,
+    one ncclAllGather on the same stream (comm = parallel.NcclComm handle; None iff n_ranks == 1) and one merge + update launch.
+    `means` is updated in place (identically on every rank).  Returns dict(means_pre, costs (local), grad)."""
+    lib = _lib.load()
+    B, NP, T, d, S = shape_local.B, shape_local.G * shape_local.K, shape_local.T, 2 * shape_local.n_dof, shape_local.S
+    _req(means, "means", None, (B, NP, T, d))
+    dt, dev = means.dtype, means.device
+    stats_local = torch.empty(B, NP, T * d + 2, dtype=dt, device=dev)
+    stats_all = torch.empty(n_ranks, B, NP, T * d + 2, dtype=dt, device=dev) if n_ranks > 1 else None
+    out = dict(means_pre=torch.empty_like(means) if want_means_pre else None,
+               costs=torch.empty(B, NP, S, dtype=dt, device=dev) if want_costs else None,
+               grad=torch.empty_like(means) if want_grad else None)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sgpmp_iterate_split_particles(C.byref(shape_local), C.byref(desc), _ptr(tables), float(step_size), int(n_iters),
+                                                     int(seed) & (2 ** 64 - 1), int(draw0), _ptr(means), _ptr(out["means_pre"]),
+                                                     C.c_void_p(comm) if comm else None, int(n_ranks), _ptr(stats_local), _ptr(stats_all),
+                                                     _ptr(out["costs"]), _ptr(out["grad"]), _stream()), "sgpmp_iterate_split_particles")
+    out["_keepalive"] = (stats_local, stats_all)      # the launches are asynchronous: keep the exchange buffers until the caller is done
+    return out
+
+
 def merge_stats(stats_list):
     """Log-sum-exp merge of per-rank (m, Z, A) statistics (the arithmetic of the split-mode exchange;
     torch.distributed all_gather supplies `stats_list` across ranks).  Pure tensor glue on any device."""

@@ -40,6 +40,58 @@ def allreduce_stats(stats, group=None):
     return merge_stats(bufs)
 
 
+class NcclComm:
+    """NCCL communicator owned by libsgpmp.so (csrc/sgpmp_nccl.cu) for the ranks of a torch.distributed group: rank 0 draws the
+    unique id in C, torch.distributed carries its 128 bytes to the other ranks, every rank calls ncclCommInitRank in C.  The
+    split-particle exchange is then issued from C on the compute stream (ops.iterate_split_particles) — torch.distributed is
+    plumbing for the rendezvous only.  One communicator per (group, device) is cached."""
+
+    _cache = {}
+
+    def __init__(self, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.handle = None
+        if self.world == 1:
+            return
+        try:       # name the NCCL that torch itself uses (bundled in the wheel), so that one copy serves both
+            import nvidia.nccl
+            import os
+            cand = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2")
+            _lib.check(lib.sgpmp_nccl_load(cand.encode() if os.path.exists(cand) else None), "sgpmp_nccl_load")
+        except ImportError:
+            _lib.check(lib.sgpmp_nccl_load(None), "sgpmp_nccl_load")
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check(lib.sgpmp_comm_unique_id(C.cast(buf, C.c_void_p)), "sgpmp_comm_unique_id")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        obj = [uid.tolist()]
+        dist.broadcast_object_list(obj, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(obj[0])
+        handle = C.c_void_p()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            idbuf = C.create_string_buffer(raw, 128)
+            _lib.check(lib.sgpmp_comm_init(C.cast(idbuf, C.c_void_p), self.rank, self.world, C.byref(handle)), "sgpmp_comm_init")
+        self.handle = handle.value
+
+    @classmethod
+    def for_group(cls, group=None, device=None):
+        key = (id(group) if group is not None else None, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, device)
+        return cls._cache[key]
+
+    def destroy(self):
+        if self.handle:
+            from . import _lib
+            _lib.load().sgpmp_comm_destroy(self.handle)
+            self.handle = None
+
+
 class StreamShards:
     """Host-to-host pipelining on ONE GPU: the shards of a problem batch (one StochGPMPBatch each, built by the caller with
     `problem_offset` = start of the shard, so every result is bit-identical to the unsharded batch) run on their own CUDA

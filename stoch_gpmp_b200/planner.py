@@ -349,17 +349,23 @@ class StochGPMPBatch:
         mp = out['means_pre']
         return (self._out(mp[..., :n]), self._out(mp[..., -n:]), pos_s, vel_s, self._out(out['costs']), self._out(out['grad']))
 
-    def optimize_split(self, opt_iters=None, group=None, **observation):
+    def optimize_split(self, opt_iters=None, group=None, return_samples=False, **observation):
         """Split-particle mode (SURVEY §8e): the S samples of every particle are divided over the ranks of `group`;
         this rank draws and scores samples [rank*S/R, (rank+1)*S/R) (RNG streams are keyed by GLOBAL sample index,
-        so the union over ranks is exactly the single-GPU sample set), then ONE all_gather of the per-particle
-        statistics (m, Z, A) per iteration replaces the softmax reduction, and every rank applies the same update.
-        Returns (pos means before the last update, vel means, local pos samples, local vel samples, local costs, grad)."""
+        so the union over ranks is exactly the single-GPU sample set).  Per iteration: one fused launch (sample -> cost ->
+        local softmax statistics, nothing materialised), ONE ncclAllGather of the per-particle (m, Z, A) blocks issued from C
+        on the compute stream, one launch that merges them by log-sum-exp and applies the update identically on every rank.
+        All iterations are enqueued by one call (ops.iterate_split_particles); the arithmetic split is planner.py:263-275.
+        Returns (pos means before the last update, vel means, local pos samples, local vel samples, local costs, grad);
+        the two sample entries are None unless return_samples (they are then regenerated from the RNG counters)."""
         import torch.distributed as dist
         from . import parallel
         if opt_iters is None:
             opt_iters = self.opt_iters
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            world, rank = 1, 0
         if self.num_samples % world:
             raise ValueError("num_samples=%d is not divisible by the %d ranks of the group" % (self.num_samples, world))
         s_loc = self.num_samples // world
@@ -367,17 +373,18 @@ class StochGPMPBatch:
         desc = self._desc(observation)
         sh_loc = ops.make_shape(self.num_problems, self.num_goals, self.num_particles_per_goal, s_loc, self.traj_len, n,
                                 self.dtype, self.problem_offset, sample_gid0=rank * s_loc)
-        for _ in range(opt_iters):
-            means_pre = self._means.clone()
-            xs, eps = ops.sample(sh_loc, self._tables, self._means, seed=self.seed, draw=self._draw, want_eps=True)
-            self._draw += 1
-            costs = ops.cost(sh_loc, desc, self._tables, xs, self._means)
-            stats = ops.local_stats(sh_loc, self.temperature, costs, eps)
-            merged = parallel.allreduce_stats(stats, group).contiguous()
-            grad = ops.apply_stats(self._shape(), self._tables, self.step_size, merged, self._means)
-        ss = xs.permute(0, 1, 4, 2, 3)
-        return (self._out(means_pre[..., :n]), self._out(means_pre[..., -n:]), self._out(ss[..., :n]), self._out(ss[..., -n:]),
-                self._out(costs), self._out(grad))
+        comm = parallel.NcclComm.for_group(group, self.device).handle if world > 1 else None
+        out = ops.iterate_split_particles(sh_loc, desc, self._tables, self.step_size, opt_iters, self._means, self.seed, self._draw,
+                                          comm=comm, n_ranks=world)
+        self._draw += opt_iters
+        self._split_keepalive = out["_keepalive"]
+        pos_s = vel_s = None
+        if return_samples:
+            xs = ops.sample(sh_loc, self._tables, out["means_pre"], seed=self.seed, draw=self._draw - 1)
+            ss = xs.permute(0, 1, 4, 2, 3)
+            pos_s, vel_s = self._out(ss[..., :n]), self._out(ss[..., -n:])
+        mp = out["means_pre"]
+        return (self._out(mp[..., :n]), self._out(mp[..., -n:]), pos_s, vel_s, self._out(out["costs"]), self._out(out["grad"]))
 
     def get_recent_samples(self):
         """planner.py:330-337: (position samples, velocity samples) of the last iteration, fresh tensors."""

@@ -563,6 +563,55 @@ def test_fused_ragged_shapes_equal_separate_kernels(n, T, S, G, K, dtype, cuda):
     assert float((out['weights'].sum(-1) - 1).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("name,R", [("panda_soft_f64", 4), ("panda_soft_f32", 2), ("planar_soft_f64", 8), ("panda_self_f32", 4)])
+def test_split_particle_fused_equals_fused_iterate(name, R, cuda):
+    """Split-particle mode emulated on ONE GPU: R 'ranks' run sgpmp_iterate_stats over their slices of every particle's samples
+    (global sample ids keep the RNG stream), the R (m, Z, A) blocks are merged by log-sum-exp INSIDE sgpmp_merge_apply_stats,
+    and the resulting means equal the single-launch fused iteration on all samples (planner.py:263-275 is what is being split).
+    The same code with ncclAllGather between the two launches is tests/test_gpu_multi.py / bench.py --gpus N."""
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dt = torch.float32 if f32 else torch.float64
+    T, n, G, K, S = spec['T'], spec['n_dof'], spec['G'], spec['K'], spec['S']
+    assert S % R == 0
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dt)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dt).unsqueeze(0) if 'spheres' in spec else None
+    desc = low.desc(spec['temperature'], sp)
+    pre = 'sameL_' if f32 else ''
+    mu = torch.tensor(g[pre + 'it0_means_pre'][None], device=cuda)
+    sh = _ops().make_shape(1, G, K, S, T, n, dt)
+    for it in range(2):
+        mu_f = mu.clone()
+        out = _ops().iterate(sh, desc, tab, spec['step_size'], 1, mu_f, seed=29, draw0=it)
+        stats, costs = [], []
+        for r in range(R):
+            shr = _ops().make_shape(1, G, K, S // R, T, n, dt, sample_gid0=r * (S // R))
+            st, c = _ops().iterate_stats(shr, desc, tab, mu, seed=29, draw=it, want_costs=True)
+            stats.append(st)
+            costs.append(c)
+        c_all = torch.cat(costs, dim=-1)
+        assert float((c_all - out['costs']).abs().max() / out['costs'].abs().max()) < (1e-6 if f32 else 1e-13)
+        mu_s = mu.clone()
+        grad = _ops().merge_apply_stats(sh, tab, spec['step_size'], torch.stack(stats, 0).contiguous(), mu_s)
+        # the softmax amplifies fp32 cost rounding (|c|/tau up to 1e2..1e3 in the soft goldens): fp32 is held to 1e-4
+        assert float((grad - out['grad']).abs().max() / out['grad'].abs().max()) < (1e-3 if f32 else 1e-9)
+        assert float((mu_s - mu_f).abs().max() / mu_f.abs().max()) < (1e-4 if f32 else 1e-10)
+        # the torch restatement of the merge (parallel.allreduce_stats, used by the gloo CPU test) agrees with the kernel
+        mu_t = mu.clone()
+        _ops().apply_stats(sh, tab, spec['step_size'], _ops().merge_stats(stats).contiguous(), mu_t)
+        assert float((mu_t - mu_s).abs().max() / mu_s.abs().max()) < (1e-6 if f32 else 1e-13)
+        mu = mu_f
+    # n iterations enqueued by ONE call of the split-mode driver with a single rank == the fused loop
+    mu_a = torch.tensor(g[pre + 'it0_means_pre'][None], device=cuda)
+    mu_b = mu_a.clone()
+    o = _ops().iterate_split_particles(sh, desc, tab, spec['step_size'], 3, mu_a, 29, 0)
+    _ops().iterate(sh, desc, tab, spec['step_size'], 3, mu_b, seed=29, draw0=0)
+    assert float((mu_a - mu_b).abs().max() / mu_b.abs().max()) < (2e-3 if f32 else 1e-9)
+    assert o['means_pre'] is not None and o['costs'].shape == (1, G * K, S)
+
+
 @pytest.mark.parametrize("n,S", [(2, 512), (7, 256), (7, 300)])
 def test_cluster_mode_equals_separate_kernels(n, S, cuda):
     """Few problems (B*NP*8 <= 296 CTAs) with S >= 256 run the fused loop in thread-block-CLUSTER mode: a particle's

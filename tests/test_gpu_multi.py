@@ -1,7 +1,8 @@
 """GPU, 2 devices, NCCL: the two multi-GPU modes against the single-GPU result (skipped on a 1-GPU box).
 
   * problem sharding: each rank runs its slice with problem_offset; gathered means == one-GPU batch, bit for bit.
-  * split-particle: each rank scores half of every particle's samples; one all_gather of (m, Z, A) per iteration;
+  * split-particle: each rank scores half of every particle's samples; one ncclAllGather of (m, Z, A) per iteration, issued
+    from C on the compute stream (csrc/sgpmp_nccl.cu);
     means == the one-GPU fused loop (fp64: 1e-9).
 """
 import os
@@ -61,7 +62,7 @@ def _worker(rank, world, port, q):
     sharded = parallel.gather_problem_results(pl.particle_means, B)
     # split-particle (fp64): every rank holds all problems, half of the samples
     ps, obs2 = _build(dev, torch.float64, B, 0, B, S)
-    out = ps.optimize_split(opt_iters=3, **obs2)
+    out = ps.optimize_split(opt_iters=3, return_samples=True, **obs2)
     q.put((rank, sharded.cpu().numpy(), ps.particle_means.cpu().numpy(), tuple(out[2].shape)))
     dist.barrier()
     dist.destroy_process_group()
