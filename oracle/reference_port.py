@@ -187,9 +187,10 @@ class ReferencePort:
         return samples, costs, w, grad
 
 
-def time_port(spec, dtype, n_problems, iters, warmup=1, fk=None, threads=None):
-    """Seconds per optimize() iteration of ONE problem on CPU (mean over `n_problems` sequential problems,
-    `iters` timed iterations each after `warmup`).  Used by bench.py (cpu_baseline / --impl reference)."""
+def time_port(spec, dtype, n_problems, iters, warmup=1, fk=None, threads=None, device="cpu"):
+    """Seconds per optimize() iteration of ONE problem (mean over `n_problems` sequential problems, `iters` timed
+    iterations each after `warmup`).  Used by bench.py (cpu_baseline / --impl reference; device="cuda:0" is the
+    informational --impl reference-cuda arm: the same dense formulation on stock torch CUDA ops)."""
     import time
     import os
     from . import prior as P
@@ -197,16 +198,22 @@ def time_port(spec, dtype, n_problems, iters, warmup=1, fk=None, threads=None):
         torch.set_num_threads(threads)
     else:
         torch.set_num_threads(os.cpu_count() or 1)
+    cuda = str(device).startswith("cuda")
     total, count = 0.0, 0
-    for b in range(n_problems):
-        port = ReferencePort(spec, dtype=dtype, fk=fk)
-        mu0 = P.const_vel_trajectories(spec['start'], spec['goals'], spec['dt'], spec['T'], spec['n_dof'], spec['K'])
-        port.set_mean(torch.as_tensor(mu0, dtype=dtype))
-        for it in range(warmup + iters):
-            t0 = time.perf_counter()
-            port.iterate()
-            t1 = time.perf_counter()
-            if it >= warmup:
-                total += t1 - t0
-                count += 1
+    with torch.device(device):
+        for b in range(n_problems):
+            port = ReferencePort(spec, dtype=dtype, fk=fk)
+            mu0 = P.const_vel_trajectories(spec['start'], spec['goals'], spec['dt'], spec['T'], spec['n_dof'], spec['K'])
+            port.set_mean(torch.as_tensor(mu0, dtype=dtype))
+            for it in range(warmup + iters):
+                if cuda:
+                    torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                port.iterate()
+                if cuda:
+                    torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                if it >= warmup:
+                    total += t1 - t0
+                    count += 1
     return total / count, torch.get_num_threads()
