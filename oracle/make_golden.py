@@ -34,7 +34,11 @@ def _np(t):
 def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_sigmas, cost_sigmas,
              temperature, step_size, iters, map_params=None, spheres=None, initial_particle_means=None,
              sigma_coll=None, sigma_goal_prior=None, store_L=True, self_field=None, field_type='rbf', clamp_sdf=False,
-             interp=None, self_interp=None, ee_goal=None, gp_trajectory=False):
+             interp=None, self_interp=None, ee_goal=None, gp_trajectory=False, compact=False):
+    """compact=True (full-size shapes, e.g. the C3 shape T=64, S=256): the big arrays — eps, samples, reset draws, dense Sigma_inv / L —
+    are NOT stored; instead the torch CPU generator state before each draw is (5 KB), from which a test re-draws the identical eps
+    (`torch.set_rng_state(...); torch.empty(S, NP, M).normal_()`: bit-exact for the same torch build), plus the first 2 samples of
+    every particle for a direct sample check."""
     ref = ref_loader.load()
     ta = {'device': torch.device('cpu'), 'dtype': dtype}
     start_state = torch.tensor(start, **ta)
@@ -135,12 +139,14 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
         torch.set_rng_state(st0)
         if initial_particle_means is None:
             rec[tag + 'init_eps'] = _np(torch.empty(K, NP // K, M, dtype=dtype).normal_())       # [K, G, M]
-        rec[tag + 'reset_discard_eps'] = _np(torch.empty(S, NP, M, dtype=dtype).normal_())
+        discard = _np(torch.empty(S, NP, M, dtype=dtype).normal_())
         assert torch.equal(torch.get_rng_state(), st_after_reset)
         rec[tag + 'means_reset'] = _np(planner.particle_means)
-        rec[tag + 'state_samples_reset'] = _np(planner.state_samples)
-        rec[tag + 'Sigma_inv'] = _np(planner.Sigma_inv)
-        if store_L:
+        if not compact:
+            rec[tag + 'reset_discard_eps'] = discard
+            rec[tag + 'state_samples_reset'] = _np(planner.state_samples)
+            rec[tag + 'Sigma_inv'] = _np(planner.Sigma_inv)
+        if store_L and not compact:
             rec[tag + 'L'] = _np(planner._sample_dist.dist._unbroadcasted_scale_tril[0])
 
         for it in range(iters):
@@ -159,9 +165,14 @@ def run_case(name, *, n_dof, T, dt, G, K, S, dtype, seed, start, goals, planner_
             x_chk = x_chk.view(S, NP, T, 2 * n_dof).transpose(1, 0)
             assert torch.equal(x_chk, samples), "eps reproduction is not bit-exact"
             pre = f'it{it}_'
-            rec[tag + pre + 'eps'] = _np(eps)                           # [S, NP, M]  (reference layout)
             rec[tag + pre + 'means_pre'] = means_pre
-            rec[tag + pre + 'samples'] = _np(samples)                   # [NP, S, T, d]
+            if compact:
+                rec[tag + pre + 'rng_state'] = st.numpy().copy()        # eps = set_rng_state(this); empty(S, NP, M).normal_()
+                rec[tag + pre + 'samples_head'] = _np(samples[:, :2])   # [NP, 2, T, d]
+                rec[tag + pre + 'eps_head'] = _np(eps[:2])              # [2, NP, M] guards the re-draw itself
+            else:
+                rec[tag + pre + 'eps'] = _np(eps)                       # [S, NP, M]  (reference layout)
+                rec[tag + pre + 'samples'] = _np(samples)               # [NP, S, T, d]
             rec[tag + pre + 'costs'] = _np(costs)                       # [NP, S]
             rec[tag + pre + 'grad'] = _np(grad)
             rec[tag + pre + 'weights'] = _np(planner._weights).reshape(NP, S)
@@ -368,6 +379,20 @@ def main(only=None):
                  cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
                  temperature=200., step_size=0.5, iters=1, spheres=panda_spheres(4, 7), self_field=(0.15, 0.1),
                  interp=(3, (5, 7)), self_interp=(2, (3, 6)))
+    # BASELINE shape (C3: 4 goals x K = 1, T = 64, n = 7; S = 256) with the shipped Panda sigmas and 5 spheres, fp64, compact
+    # record (see run_case): pins the full-size shape by the reference itself, not only by the numpy restatement
+    run_case('c3_panda_f64', n_dof=7, T=64, dt=0.05, G=4, K=1, S=256, dtype=torch.float64, seed=21,
+             start=PANDA_START, goals=panda_goals(4, 0), planner_sigmas=PANDA_SIGMAS, initial_particle_means='const_vel',
+             cost_sigmas=dict(sigma_start=0.0001, sigma_gp=0.0007), sigma_coll=0.01, sigma_goal_prior=20.,
+             temperature=1., step_size=0.1, iters=2, spheres=panda_spheres(5, 0), compact=True)
+    # the same shape with soft sigmas (live softmax weights at full size)
+    run_case('c3_panda_soft_f64', n_dof=7, T=64, dt=0.05, G=4, K=1, S=256, dtype=torch.float64, seed=22,
+             start=[0.05 * v for v in PANDA_START], goals=[[0.05 * v for v in g] for g in panda_goals(4, 3)],
+             planner_sigmas=dict(sigma_start_init=0.5, sigma_goal_init=0.5, sigma_gp_init=0.8,
+                                 sigma_start_sample=4.0, sigma_goal_sample=4.0, sigma_gp_sample=0.5),
+             initial_particle_means='const_vel',
+             cost_sigmas=dict(sigma_start=0.5, sigma_gp=0.5), sigma_coll=0.3, sigma_goal_prior=20.,
+             temperature=200., step_size=0.5, iters=1, spheres=panda_spheres(5, 3), compact=True)
 
 
 if __name__ == '__main__':

@@ -39,6 +39,7 @@ struct CostSmem {
 };
 
 constexpr int SPH_STRIDE = 8;
+constexpr int SPH_ORIGIN = SPH_STRIDE * SGPMP_MAX_SPHERES + 4;     // (ox, oy, oz, -) of the shifted RBF frame, 16-byte aligned
 
 // 4 consecutive reals from a 16-byte (fp32) / 32-byte (fp64) aligned shared-memory address in one LDS
 __device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
@@ -52,9 +53,11 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 
 // Stage one sphere (cx, cy, cz, r) into the shared table row.
 // mode != SGPMP_FIELD_RBF: slot 3 holds the radius itself (the sdf / occupancy variants need |p - c| and r).
+// (ox, oy, oz): origin of the SHIFTED frame the structured chain code evaluates the RBF in (see stage_cta_constants);
+// zero for every other path.
 template <typename real>
-__device__ __forceinline__ void stage_sphere(const real* s4, real* row, int mode) {
-    const double cx = s4[0], cy = s4[1], cz = s4[2], r = s4[3];
+__device__ __forceinline__ void stage_sphere(const real* s4, real* row, int mode, double ox = 0.0, double oy = 0.0, double oz = 0.0) {
+    const double cx = (double)s4[0] - ox, cy = (double)s4[1] - oy, cz = (double)s4[2] - oz, r = s4[3];
     if (mode != SGPMP_FIELD_RBF) {
         row[0] = (real)cx; row[1] = (real)cy; row[2] = (real)cz; row[3] = (real)r;
         row[4] = row[5] = row[6] = row[7] = 0;
@@ -220,9 +223,10 @@ struct Cols {   // rotation columns a, b, c
 };
 
 // Origins of the 6 q-dependent, distinct link frames of the Panda structure; weights {1,1,2,1,2,1}.
+// o3: origin of the shifted frame (stage_cta_constants); every origin comes out as p - o at no extra instruction.
 template <typename V>
 __device__ __forceinline__ void fk_panda_origins(const CostParams<typename VT<V>::real>& P, const V* q, V (&X)[PANDA_EVAL_LINKS],
-                                                 V (&Y)[PANDA_EVAL_LINKS], V (&Z)[PANDA_EVAL_LINKS]) {
+                                                 V (&Y)[PANDA_EVAL_LINKS], V (&Z)[PANDA_EVAL_LINKS], const typename VT<V>::real* o3) {
     using real = typename VT<V>::real;
     // joints 1 and 2 by hand (R starts as the identity; frame 0: t = (0,0,d1); frame 1: t = 0, Rx(-90)):
     //   a = (c1 c0, c1 s0, -s1), b = (-s1 c0, -s1 s0, -c1), c = (-s0, c0, 0),  p = (0, 0, d1)
@@ -231,7 +235,7 @@ __device__ __forceinline__ void fk_panda_origins(const CostParams<typename VT<V>
     vsincos(q[1], &s1, &c1);
     const real d1 = P.p[0][2], t2y = P.p[2][1];
     const V s1c0 = s1 * c0, s1s0 = s1 * s0;
-    V px = (-t2y) * s1c0, py = (-t2y) * s1s0, pz = vfma(-t2y, c1, d1);          // frame 2: p += t2y * b
+    V px = vfma(-t2y, s1c0, -o3[0]), py = vfma(-t2y, s1s0, -o3[1]), pz = vfma(-t2y, c1, d1 - o3[2]);          // frame 2: p += t2y * b
     X[0] = px; Y[0] = py; Z[0] = pz;               // link3
     // frame 2 rotation Rx(+90): (a, b, c) -> (a, c, -b)
     Cols<V> R;
@@ -280,7 +284,7 @@ struct TrajCost {
         if constexpr (CHAIN >= 1) {
             static_assert(N == 7, "Panda structure has 7 joints");
             V X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS], PP[PANDA_EVAL_LINKS];
-            fk_panda_origins<V>(P, q, X, Y, Z);
+            fk_panda_origins<V>(P, q, X, Y, Z, sm.sph + SPH_ORIGIN);
 #pragma unroll
             for (int l = 0; l < PANDA_EVAL_LINKS; ++l) PP[l] = vfma(X[l], X[l], vfma(Y[l], Y[l], Z[l] * Z[l]));
             // (the sdf / occupancy variants of the sphere field, costs/fields.py:80-86, always take the generic chain code:
@@ -525,7 +529,7 @@ struct TrajCost {
 
 // Per-CTA staging of the problem constants into shared memory: start [d], goal [d] of goal index g, the sphere
 // table [MAX_SPHERES][8] followed by one slot for coll_const.  Ends with a __syncthreads().
-constexpr int SPH_SMEM = SPH_STRIDE * SGPMP_MAX_SPHERES + 4;   // keeps what follows 16-byte aligned
+constexpr int SPH_SMEM = SPH_STRIDE * SGPMP_MAX_SPHERES + 8;   // + coll_const, self_const, -, -, origin[3], -  (keeps what follows 16-byte aligned)
 
 // VOFF: offset of the velocity half inside the staged start/goal rows (N = dense; the dof-pair kernels pad it).
 template <typename real, int N, int CHAIN, int VOFF = N>
@@ -539,19 +543,38 @@ __device__ __forceinline__ void stage_cta_constants(const CostParams<real>& P, i
         start[c] = P.start[(size_t)b * d + k];
         goal[c] = P.has_goal ? P.goals[((size_t)b * G + g) * d + k] : (real)0;
     }
+    // Structured chains evaluate k |p - c|^2 in the EXPANDED form k |p|^2 + a.p + b (4 FMA per link-sphere pair).  Its terms are
+    // ~k |c|^2 each and cancel down to k d^2, so in fp32 the exponent carries ~|k| |c|^2 2^-23 of rounding (3e-5 of the term with the
+    // shipped scene seen from the robot base).  The cure costs nothing per sample: a frame whose origin is the centroid of the spheres
+    // — where the exponentials that matter live — makes |c| and |p| there a few sphere radii; the origin is folded into the first
+    // link offset of the chain (fk_panda_origins), so every link origin comes out already shifted.  (The self-collision code of
+    // CHAIN 2 uses base-frame expressions for the q-independent links: no shift there.)
+    if (threadIdx.x == 0) {
+        double ox = 0, oy = 0, oz = 0;
+        if (CHAIN == 1 && P.has_spheres && !P.has_self && P.sphere_mode == SGPMP_FIELD_RBF && P.n_spheres > 0) {
+            const real* s4 = P.spheres + (size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres * 4;
+            for (int k = 0; k < P.n_spheres; ++k) { ox += s4[4 * k]; oy += s4[4 * k + 1]; oz += s4[4 * k + 2]; }
+            ox /= P.n_spheres; oy /= P.n_spheres; oz /= P.n_spheres;
+        }
+        sph[SPH_ORIGIN] = (real)ox; sph[SPH_ORIGIN + 1] = (real)oy; sph[SPH_ORIGIN + 2] = (real)oz; sph[SPH_ORIGIN + 3] = 0;
+    }
+    __syncthreads();
+    const double ox = sph[SPH_ORIGIN], oy = sph[SPH_ORIGIN + 1], oz = sph[SPH_ORIGIN + 2];     // the ROUNDED origin is the one the chain subtracts
     if (P.has_spheres)
         for (int k = threadIdx.x; k < P.n_spheres; k += blockDim.x)
-            stage_sphere<real>(P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4, sph + SPH_STRIDE * k, P.sphere_mode);
+            stage_sphere<real>(P.spheres + ((size_t)(P.spheres_per_problem ? b : 0) * P.n_spheres + k) * 4, sph + SPH_STRIDE * k, P.sphere_mode,
+                               ox, oy, oz);
     __syncthreads();
     if (threadIdx.x == 0) {
         real cc = 0;
         if (CHAIN >= 1 && P.has_spheres && P.sphere_mode == SGPMP_FIELD_RBF) {
-            // q-independent origins of the Panda structure: base (if counted), link1 and link2 at (0, 0, z0)
+            // q-independent origins of the Panda structure: base (if counted), link1 and link2 at (0, 0, z0), in the shifted frame
             const real z0 = P.p[0][2];
+            const real bx = (real)-ox, by = (real)-oy, bz = (real)-oz, lz = z0 - (real)oz;
             for (int o = 0; o < P.n_spheres; ++o) {
                 const real* s = sph + SPH_STRIDE * o;
-                if (P.include_base) cc += vexp2_fast(s[7]);
-                cc += (real)2 * vexp2_fast(z0 * s[6] + (s[3] * z0 * z0 + s[7]));
+                if (P.include_base) cc += vexp2_fast(s[3] * (bx * bx + by * by + bz * bz) + (s[4] * bx + s[5] * by + s[6] * bz) + s[7]);
+                cc += (real)2 * vexp2_fast(s[3] * (bx * bx + by * by + lz * lz) + (s[4] * bx + s[5] * by + s[6] * lz) + s[7]);
             }
         }
         sph[SPH_STRIDE * SGPMP_MAX_SPHERES] = cc;

@@ -48,7 +48,10 @@ struct TrajCostPairs {
             const float d1 = P.p[0][2], t2y = P.p[2][1];
             const float s1c0 = s1 * c0, s1s0 = s1 * s0;
             float X[PANDA_EVAL_LINKS], Y[PANDA_EVAL_LINKS], Z[PANDA_EVAL_LINKS];
-            float px = -t2y * s1c0, py = -t2y * s1s0, pz = fmaf(-t2y, c1, d1);
+            // origins come out in the shifted RBF frame (stage_cta_constants): p - o, folded into the first link offset
+            float ox, oy, oz, o_unused;
+            load4(sm.sph + SPH_ORIGIN, ox, oy, oz, o_unused);
+            float px = fmaf(-t2y, s1c0, -ox), py = fmaf(-t2y, s1s0, -oy), pz = fmaf(-t2y, c1, d1 - oz);
             X[0] = px; Y[0] = py; Z[0] = pz;                                   // link3
             Cols<float> R;
             R.ax = c1 * c0; R.ay = c1 * s0; R.az = -s1;

@@ -7,7 +7,8 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 GOLDEN_GPMP = [g for g in _ALL if g.startswith("gpmp_")]          # runs of the reference's Gauss-Newton GPMP planner
-GOLDEN = [g for g in _ALL if not g.startswith("gpmp_")]           # runs of StochGPMP
+GOLDEN_C3 = [g for g in _ALL if g.startswith("c3_")]              # full-size (T = 64, S = 256) runs of StochGPMP, compact records
+GOLDEN = [g for g in _ALL if not g.startswith("gpmp_") and not g.startswith("c3_")]           # runs of StochGPMP
 GOLDEN_F64 = [g for g in GOLDEN if g.endswith("f64") or g.endswith("f64_T64")]
 GOLDEN_F32 = [g for g in GOLDEN if g.endswith("f32")]
 
@@ -30,6 +31,22 @@ def n_iters(g, prefix=""):
     while f"{prefix}it{it}_eps" in g.files:
         it += 1
     return it
+
+
+def eps_from_rng_state(g, pre, dtype=None):
+    """Compact records (oracle/make_golden.py run_case(compact=True)): re-draw the eps the reference drew from the torch CPU
+    generator state stored before the draw.  Returns [S, NP, M] (torch draw layout) and checks its head against the record."""
+    import torch
+    S, NP, M = int(g['S']), int(g['G']) * int(g['K']), int(g['T']) * 2 * int(g['n_dof'])
+    keep = torch.get_rng_state()
+    try:
+        torch.set_rng_state(torch.from_numpy(g[pre + 'rng_state'].copy()))
+        eps = torch.empty(S, NP, M, dtype=dtype or getattr(torch, str(g['dtype']))).normal_().numpy()
+    finally:
+        torch.set_rng_state(keep)
+    if not np.array_equal(eps[:2], g[pre + 'eps_head']):
+        raise AssertionError("the torch CPU generator does not reproduce the recorded draw (different torch build?)")
+    return eps
 
 
 def rel(a, b):
