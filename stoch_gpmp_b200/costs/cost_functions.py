@@ -291,6 +291,8 @@ class LoweredCost:
             if obstacle_spheres is None:
                 # the reference's LinkDistanceField.compute_cost returns 0 without spheres (fields.py:64-65)
                 d.spheres, d.n_spheres = None, 0
+                self._spheres_src = None        # the next call WITH spheres must patch the descriptor again (the same
+                #                                 tensor passed after a None call used to be taken for "unchanged" -> no obstacles)
             elif obstacle_spheres is not self._spheres_src:
                 sp = torch.as_tensor(obstacle_spheres).to(device=self.device, dtype=self.dtype)
                 if sp.dim() == 2:

@@ -47,6 +47,16 @@ class GPMPBatch(StochGPMPBatch):
 
     def reset(self, start_state=None, multi_goal_states=None, initial_particle_means=None, _init_eps=None):
         super().reset(start_state, multi_goal_states, initial_particle_means, _init_eps=_init_eps)
+        # The reference's GPMP builds its sampling distribution WITHOUT goal_states (planner.py:533-539): MultiMPPrior is then not
+        # goal-directed and Sigma^-1 carries no goal block, so sample_trajectories() is not pinned at the goal.
+        if self.goal_directed:
+            self.goal_directed = False
+            try:
+                self._tables, (self._D, self._O) = self._factor(self.sigma_start_sample, self.sigma_gp_sample, None, "sampling")
+            finally:
+                self.goal_directed = True
+            self._Sigma_inv = None
+            self._state_samples = None
         low = self._lowered
         if low is None:
             raise NotImplementedError("GPMP needs a CostComposite (cost=...)")

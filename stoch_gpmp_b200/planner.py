@@ -87,7 +87,9 @@ class StochGPMPBatch:
                                "no CPU fallback" % dev)
         _lib.load()                                   # fail loudly if the CUDA library is missing
         self.device, self.dtype = dev, tensor_args['dtype']
-        self.seed = int(seed) if seed is not None else int(torch.initial_seed()) & 0x7fffffffffffffff
+        # seed=None: the key is DRAWN from torch's global generator: unseeded planners / repeated trials get independent
+        # noise as with the reference (which consumes the global generator), and torch.manual_seed() still makes a run reproducible
+        self.seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         self._draw = 0
 
         self.n_dof = n_dof
@@ -346,6 +348,11 @@ class StochGPMPBatch:
             self._state_samples = ss
             self._samples_sminor = out['samples']
             pos_s, vel_s = self._out(ss[..., :n]), self._out(ss[..., -n:])
+        elif _eps is None:
+            # nothing was written: `state_samples` (and _get_traj) regenerate THIS iteration's samples lazily from the RNG
+            # counters, so that they always pair with the weights of the same iteration
+            self._state_samples = None
+            self._state_samples_src = (out['means_pre'], self._draw - 1, self.num_samples)
         mp = out['means_pre']
         return (self._out(mp[..., :n]), self._out(mp[..., -n:]), pos_s, vel_s, self._out(out['costs']), self._out(out['grad']))
 

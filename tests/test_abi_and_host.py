@@ -50,7 +50,8 @@ def test_struct_layout_matches_c(lib, tmp_path):
 
 def test_dof_support_table(lib):
     assert lib.sgpmp_dof_supported(2) == 1 and lib.sgpmp_dof_supported(7) == 1
-    assert lib.sgpmp_dof_supported(5) == 0 and lib.sgpmp_dof_supported(0) == 0
+    assert lib.sgpmp_dof_supported(5) == 1 and lib.sgpmp_dof_supported(14) == 1      # every DoF count of BASELINE's C5 sweep
+    assert lib.sgpmp_dof_supported(9) == 0 and lib.sgpmp_dof_supported(0) == 0
 
 
 def test_bad_arguments_are_reported_not_crashed(lib):

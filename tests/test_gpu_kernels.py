@@ -502,6 +502,38 @@ def test_fused_equals_separate_kernels_inkernel_rng(case, dtype, cuda):
     assert float(ess.max()) > 1.5          # the weighted pass really was exercised
 
 
+@pytest.mark.parametrize("n", [5, 14])
+def test_fused_iteration_other_dof_counts(n, cuda):
+    """n_dof 5 and 14 (the DoF counts of BASELINE's C5 sweep that round 1 could only sample): the fused loop against the
+    numpy oracle on the kernel's own eps (GP + goal factors; the reference is generic in n_dof, planner.py:51-52), fp64."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, CostGoalPrior
+    dtype = torch.float64
+    T, G, K, S, B = 12, 2, 1, 40, 2
+    d = 2 * n
+    ta = dict(device=cuda, dtype=dtype)
+    rs = np.random.RandomState(n)
+    start = rs.uniform(-0.3, 0.3, (B, d))
+    goals = rs.uniform(-0.5, 0.5, (B, G, d))
+    spec = dict(n_dof=n, T=T, dt=0.1, G=G, K=K, S=S, temperature=20.0, step_size=0.5, goals=goals[0], start=start[0],
+                sigma_start_sample=0.3, sigma_gp_sample=1.0, sigma_goal_sample=0.3, cost_sigma_start=0.5, cost_sigma_gp=2.0,
+                sigma_goal_prior=1.0, sigma_coll=None)
+    tab = _tables(spec, cuda)
+    comp = CostComposite(n, T, [CostGP(n, T, torch.tensor(start, **ta), 0.1, dict(sigma_start=0.5, sigma_gp=2.0), ta),
+                                CostGoalPrior(n, T, multi_goal_states=torch.tensor(goals, **ta), num_particles_per_goal=K, num_samples=S,
+                                              sigma_goal_prior=1.0, tensor_args=ta)], tensor_args=ta)
+    desc = comp.lower(B, G, cuda, dtype).desc(20.0, None)
+    sh = _ops().make_shape(B, G, K, S, T, n, dtype)
+    mu = torch.tensor(rs.uniform(-0.5, 0.5, (B, G * K, T, d)), **ta)
+    mu_f = mu.clone()
+    out = _ops().iterate(sh, desc, tab, 0.5, 1, mu_f, seed=5, draw0=2)
+    _, eps = _ops().sample(sh, tab, mu, seed=5, draw=2, want_eps=True)
+    eps = from_sminor(eps.cpu().numpy())
+    for b in range(B):
+        r = OP.iterate(dict(spec, start=start[b], goals=goals[b]), mu[b].cpu().numpy(), eps[b])
+        assert rel(out['costs'][b].cpu().numpy(), r['costs']) < 1e-10
+        assert rel(mu_f[b].cpu().numpy(), r['means_post']) < 1e-10
+
+
 def test_fused_problem_sharding_invariance(cuda):
     """B problems in one launch == the same problems launched as two shards with problem_gid0 offsets."""
     g = load('panda_soft_f32')

@@ -92,6 +92,29 @@ def test_final_plans_agree_in_cost_and_collision_freeness(cuda):
     assert np.array_equal(occ_got, occ_want)
 
 
+def test_spheres_then_none_then_same_spheres(cuda):
+    """optimize(obstacle_spheres=sp), optimize() (no spheres: the field contributes 0, fields.py:64-65), then the SAME
+    tensor again must plan WITH the obstacles again — the descriptor cache used to take the repeated tensor for 'unchanged'."""
+    g = load('panda_soft_f32')
+    spec = OP.spec_from_golden(g)
+    obs = _obs(spec, cuda, torch.float32)
+    a = _planner(g, spec, cuda, torch.float32)
+    b = _planner(g, spec, cuda, torch.float32)
+    n_sph = a._desc(obs).n_spheres
+    assert n_sph == obs['obstacle_spheres'].shape[-2]
+    c1 = a.optimize(**obs)[4]
+    a.optimize()
+    assert a._desc({}).n_spheres == 0
+    d3 = a._desc(obs)
+    assert d3.n_spheres == n_sph and d3.spheres
+    # same draws on a planner that never saw the None call: identical third iteration only if the obstacles are back
+    b.optimize(**obs)
+    b._means.copy_(a._means)
+    b._draw = a._draw
+    assert torch.equal(a.optimize(**obs)[4], b.optimize(**obs)[4])
+    assert not torch.equal(c1, a.optimize()[4])
+
+
 def test_lazy_samples_regenerate_identically(cuda):
     """return_samples=False writes nothing; get_recent_samples() rebuilds the same samples from the
     counter-based RNG; state_samples after reset is reproducible too."""
@@ -197,7 +220,7 @@ def test_error_behaviour(cuda, lib):
         pl.optimize()
     # n_dof without an instantiation
     with pytest.raises(NotImplementedError):
-        StochGPMP(1, 4, 8, 1, dt=0.1, n_dof=5, start_state=torch.zeros(10, **ta), multi_goal_states=torch.zeros(1, 10, **ta),
+        StochGPMP(1, 4, 8, 1, dt=0.1, n_dof=9, start_state=torch.zeros(18, **ta), multi_goal_states=torch.zeros(1, 18, **ta),
                   cost=None, sigma_start_init=1., sigma_start_sample=1., sigma_goal_init=1., sigma_goal_sample=1.,
                   sigma_gp_init=1., sigma_gp_sample=1., tensor_args=ta)
 
