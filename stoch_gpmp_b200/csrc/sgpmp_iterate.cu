@@ -519,6 +519,15 @@ static int launch_iterate(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
             return P.has_self ? launch_iterate_n<real, 7, 2>(sh, P, A, st) : launch_iterate_n<real, 7, 1>(sh, P, A, st);
         }
     }
+    if constexpr (sizeof(real) == 4) {
+        // no link fields (planar occupancy map / no obstacle cost): the state-only form of the record-layout kernel
+        static const char* split_env = getenv("SGPMP_ITERATE_SPLIT");
+        if (!(split_env && atoi(split_env) == 0) && !(P.has_spheres || P.has_self || P.has_ee) &&
+            (A.stats_out || iterate_cluster_size(sh, A.eps_in != nullptr) == 1)) {
+            rc = launch_iterate_split(sh, P, A, 0, st);
+            if (rc != SGPMP_ERR_UNSUPPORTED) return rc;
+        }
+    }
     switch (sh.n_dof) {
 #define SGPMP_DOF_CASE(N) case N: return launch_iterate_n<real, N, 0>(sh, P, A, st);
 #include "sgpmp_dof_list.inc"

@@ -22,9 +22,10 @@ struct IterArgs {
     real* stats_out;       // split-particle mode: [B*NP][M+2] = (m, Z, A) of this launch's samples; the update is skipped
 };
 
-// Role-split fused iteration for the Panda structure (fp32, 7 DoF, RBF link fields): sgpmp_iterate_split.cu.
-// chain = 1 (sphere field only) or 2 (+ self-collision field).  Returns SGPMP_ERR_UNSUPPORTED when the shape does
-// not fit (the caller then takes the single-role kernel).
+// Record-layout fused iteration (fp32): sgpmp_iterate_split.cu.
+// chain = 1 (Panda structure, sphere field only) or 2 (+ self-collision field): role-split, state warps + link warps;
+// chain = 0: state warps only (no link fields: planar occupancy map or no obstacle cost), n_dof 2, 3, 4, 6.
+// Returns SGPMP_ERR_UNSUPPORTED when the shape does not fit (the caller then takes the single-role kernel).
 int launch_iterate_split(const sgpmp_shape_t& sh, const CostParams<float>& P, const IterArgs<float>& A, int chain, cudaStream_t st);
 
 }  // namespace sgpmp

@@ -80,28 +80,32 @@ __device__ __forceinline__ void ld_2f2(const float* p, F2& a, F2& b) {     // on
 //   [8 + 12k .. +11]   DoF pair k:  gmu (p0 p1 v0 v1) | b (p0 p1 v0 v1) | mu (p0 p1 v0 v1)
 // gmu = mu_t - Phi mu_{t-1} (GP residual of the mean), b = Sigma^-1 mu.  One pointer walks it, every access is an
 // LDS.128/LDS.64 at an immediate offset.  The ghost DoF (odd count) holds zeros.
-constexpr int REC = 56, REC_G = 0, REC_B = 4, REC_M = 8;
+constexpr int REC_G = 0, REC_B = 4, REC_M = 8;
+__host__ __device__ constexpr int rec_floats(int n_dof) { return 8 + 12 * ((n_dof + 1) / 2); }
 __device__ __forceinline__ int rec_col(int i, int a, int what) { return 8 + 12 * (i >> 1) + what + 2 * a + (i & 1); }   // a: 0 pos, 1 vel
 
 // NA state warps + NB link warps per CTA (NA % NB == 0): 32 NA samples per sweep; link warp j serves the state warps
-// j, j + NB, ... stage by stage.  The state role is the latency-bound one (dependent Philox / MUFU chains), so it gets
-// more warps than the link role, whose stream is dense independent FFMA2 work.
+// j, j + NB, ... stage by stage.  NB = 0: no link fields (CHAIN = 0; the planar occupancy-map cost is gathered by the state
+// warps themselves) — then there is no ring and no mbarrier, just the state role with its record layout.
 template <int NA, int NB> struct SplitCfg {
     static constexpr int BS = 32 * (NA + NB), SW = 32 * NA;
-    // CTAs per SM: as many as 1024 threads (64 registers each) allow
-    static constexpr int MINB = (1024 / BS) > 0 ? (1024 / BS) : 1;
+    // CTAs per SM: with link warps as many as 1024 threads (64 registers each) allow; state-only CTAs fit 48 registers
+    static constexpr int MINB = NB ? ((1024 / BS) > 0 ? (1024 / BS) : 1) : (1280 / BS > 24 ? 24 : 1280 / BS);
     // shared-memory bytes of the region that pass 1 uses for the ring + link sums and the block phases for acc / nzl / nzo
     __host__ __device__ static constexpr size_t pass1_bytes() {
-        return (size_t)NA * SGPMP_SPLIT_NSTG * SGPMP_SPLIT_TS * 96 * sizeof(float2) + (size_t)32 * NA * 8 * sizeof(float);
+        return NB ? (size_t)NA * SGPMP_SPLIT_NSTG * SGPMP_SPLIT_TS * 96 * sizeof(float2) + (size_t)32 * NA * 8 * sizeof(float) : 0;
     }
 };
 
-template <int CHAIN, int NA, int NB>
+template <int N, int CHAIN, int NA, int NB>
 __global__ void __launch_bounds__(SplitCfg<NA, NB>::BS, SplitCfg<NA, NB>::MINB)
 iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_constant__ IterArgs<float> A) {
     using Cfg = SplitCfg<NA, NB>;
-    constexpr int N = 7, d = 14, NP2 = 4, BS = Cfg::BS, SW = Cfg::SW, R = NA / NB;
-    static_assert(NA % NB == 0, "every link warp serves the same number of state warps");
+    constexpr int d = 2 * N, NP2 = (N + 1) / 2, REC = rec_floats(N), BS = Cfg::BS, SW = Cfg::SW, R = NB ? NA / (NB ? NB : 1) : 0;
+    static_assert(NB == 0 || NA % (NB ? NB : 1) == 0, "every link warp serves the same number of state warps");
+    static_assert((CHAIN == 0) == (NB == 0), "link warps exist exactly when the chain has link fields");
+    static_assert(CHAIN == 0 || N == 7, "Panda structure has 7 joints");
+    static_assert(NP2 <= 4, "start / goal staging holds up to 8 DoF");
     constexpr int TS = SGPMP_SPLIT_TS, NSTG = SGPMP_SPLIT_NSTG, UNROLL_A = SGPMP_SPLIT_UNROLL_A;
     constexpr int SLOT = 3 * 32;                                      // float2 per (state warp, step): q pairs 0..2 x 32 lanes
     const int T = A.T, S = A.S, G = A.G, K = A.K;
@@ -114,8 +118,8 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
     float* start = red + 32;                                   // [16] pair-interleaved like the mu block of a record
     float* goal = start + 16;                                  // [16]
     double* red64 = reinterpret_cast<double*>(goal + 16);      // [32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red64 + 32);  // [NA][2 NSTG + 1]
-    unsigned char* uni = reinterpret_cast<unsigned char*>(bars + ((NA * (2 * NSTG + 1) + 1) & ~1));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red64 + 32);  // [NA][2 NSTG + 1]  (NB > 0)
+    unsigned char* uni = reinterpret_cast<unsigned char*>(bars + (NB ? ((NA * (2 * NSTG + 1) + 1) & ~1) : 0));
     // -- the union region: pass 1 ...
     float2* ring = reinterpret_cast<float2*>(uni);             // [NA][NSTG][TS][3][32]
     float* bacc = reinterpret_cast<float*>(ring + (size_t)NA * NSTG * TS * SLOT);   // [32 NA][8] link-field sums of a sweep
@@ -136,7 +140,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
     auto bar_res = [&](int w) { return bars + w * (2 * NSTG + 1) + 2 * NSTG; };
     auto pidx = [](int j) { return (j < N ? rec_col(j, 0, 0) : rec_col(j - N, 1, 0)) - 8; };   // state index -> column of a pair block
 
-    if (tid < NA * (2 * NSTG + 1)) mbar_init(bars + tid, 32);
+    if (NB > 0 && tid < NA * (2 * NSTG + 1)) mbar_init(bars + tid, 32);
     for (int k = tid; k < T * REC; k += BS) rec[k] = 0.f;
     __syncthreads();
     for (int k = tid; k < T * 8; k += BS) {
@@ -148,16 +152,17 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
         const int t = k / d, j = k - t * d;
         rec[t * REC + REC_M + 8 + pidx(j)] = A.means[(size_t)bp * M + k];
     }
-    stage_cta_constants<float, N, CHAIN, 8>(P, b, p / K, G, stg_tmp, stg_tmp + 16, sph);
-    if (tid < 32) {      // re-lay start / goal from [pos 0..7 | vel 0..7] to the pair-interleaved order (stage_cta_constants ended with a barrier)
+    stage_cta_constants<float, N, CHAIN, 2 * NP2>(P, b, p / K, G, stg_tmp, stg_tmp + 16, sph);
+    if (tid < 32) {      // re-lay start / goal from [pos pairs | vel pairs] to the pair-interleaved order (stage_cta_constants ended with a barrier)
         const int i = tid & 7, a = (tid >> 3) & 1, which = tid >> 4;
-        (which ? goal : start)[4 * (i >> 1) + 2 * a + (i & 1)] = stg_tmp[16 * which + 8 * a + i];
+        if (i < 2 * NP2) (which ? goal : start)[4 * (i >> 1) + 2 * a + (i & 1)] = stg_tmp[16 * which + 2 * NP2 * a + i];
     }
     CostSmem<float> sm;
     sm.start = start; sm.goal = goal; sm.bvec = nullptr; sm.sph = sph;
     sm.coll_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES];
     sm.self_const = sph[SPH_STRIDE * SGPMP_MAX_SPHERES + 1];
-    sm.map = nullptr; sm.map_u8 = nullptr;
+    sm.map = P.has_map ? P.occ_map + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
+    sm.map_u8 = (P.has_map && P.occ_map_u8) ? P.occ_map_u8 + (size_t)(P.map_of_problem ? P.map_of_problem[b] : 0) * P.map_h * P.map_w : nullptr;
     __syncthreads();
 
 #ifdef SGPMP_SPLIT_STAGGER_NS
@@ -220,6 +225,8 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
 #pragma unroll
                 for (int k = 0; k < NP2; ++k) yp[k] = yv[k] = f2(0.f, 0.f);
                 F2 cgp = f2(0.f, 0.f), cis = f2(0.f, 0.f), cst = f2(0.f, 0.f), cgo = f2(0.f, 0.f);
+                TrajCostPairs<N, 0> tcm;          // occupancy-map gather of the state warps (planar: obst_map.py:164-182)
+                tcm.begin();
                 auto draw = [&](int t, F2 (&ep)[NP2], F2 (&ev)[NP2]) {
                     if (eps) {
                         const float* r0 = eps + ((size_t)t * d) * S + s0;
@@ -230,10 +237,11 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                             ev[k] = f2(r0[(size_t)(N + i0) * S], i1 < N ? r0[(size_t)(N + i1) * S] : 0.f);
                         }
                     } else {
-                        normal_pair_f2<true>(key, (uint32_t)t, 0u, sgid, pgid, ep[0], ev[0], dro);
-                        normal_pair_f2<true>(key, (uint32_t)t, 1u, sgid, pgid, ep[1], ev[1], dro);
-                        normal_pair_f2<true>(key, (uint32_t)t, 2u, sgid, pgid, ep[2], ev[2], dro);
-                        normal_pair_f2<false>(key, (uint32_t)t, 3u, sgid, pgid, ep[3], ev[3], dro);
+#pragma unroll
+                        for (int k = 0; k < NP2; ++k) {
+                            if (2 * k + 1 < N) normal_pair_f2<true>(key, (uint32_t)t, (uint32_t)k, sgid, pgid, ep[k], ev[k], dro);
+                            else normal_pair_f2<false>(key, (uint32_t)t, (uint32_t)k, sgid, pgid, ep[k], ev[k], dro);
+                        }
                     }
                 };
                 auto emit_row = [&](int t) {      // last iteration only: x_t = mu_t + y_t to global memory
@@ -272,9 +280,9 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                 }
                 for (int t0 = 1; t0 < T; t0 += TS) {
                     const uint32_t stg = sc % NSTG, use = sc / NSTG;
-                    mbar_wait(bar_empty(wa, stg), (use & 1u) ^ 1u);
+                    if constexpr (NB > 0) mbar_wait(bar_empty(wa, stg), (use & 1u) ^ 1u);
                     const int tend = min(t0 + TS, T);
-                    float2* slot = ring + ((size_t)(wa * NSTG + stg) * TS) * SLOT + lane;
+                    float2* slot = NB > 0 ? ring + ((size_t)(wa * NSTG + stg) * TS) * SLOT + lane : nullptr;
                     const float* blk = rec + t0 * REC;
                     F2 cgs = f2(0.f, 0.f);          // GP sum of this stage (two-level accumulation)
 #pragma unroll UNROLL_A
@@ -303,12 +311,16 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                             cgs = vfma(e_p, vfma(P.q12x2, e_v, P.q11 * e_p), cgs);
                             cgs = vfma(P.q22 * e_v, e_v, cgs);
                             cis = vfma(yp[k], bp_, vfma(yv[k], bv_, cis));
-                            if (k < 3) st_f2(slot + 32 * k, ld_f2(blk + 8 + 12 * k + REC_M) + yp[k]);   // q_t[2k], q_t[2k+1] for the link warp
+                            if (NB > 0 && k < 3) st_f2(slot + 32 * k, ld_f2(blk + 8 + 12 * k + REC_M) + yp[k]);   // q_t[2k], q_t[2k+1] for the link warp
+                        }
+                        if (NB == 0 && P.has_map) {
+                            const F2 x01 = ld_f2(blk + 8 + REC_M) + yp[0];
+                            tcm.map_gather_deferred(P, sm, lane0(x01), lane1(x01));
                         }
                         if (emit && valid) emit_row(t);
                     }
                     cgp += cgs;
-                    mbar_arrive(bar_full(wa, stg));
+                    if constexpr (NB > 0) mbar_arrive(bar_full(wa, stg));
                     ++sc;
                 }
                 // goal prior on x_{T-1} (cost_functions.py:376-388) and the EE SE(3) goal (cost_functions.py:308-321)
@@ -325,7 +337,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                     }
                 }
                 float ee = 0.f;
-                if (P.has_ee) {
+                if (N == 7 && P.has_ee) {
                     float q[2 * NP2];
 #pragma unroll
                     for (int k = 0; k < NP2; ++k) {
@@ -338,13 +350,18 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                 const float gp = hsum(cgp);
                 const float go = hsum(cgo) * P.inv_sig_goal2;
                 const float is = (hsum(cis) + mub) * P.temperature;
-                mbar_wait(bar_res(wa), rc & 1u);
-                const float4* ba = reinterpret_cast<const float4*>(bacc + (size_t)(wa * 32 + lane) * 8);
-                const float4 v0 = ba[0], v1 = ba[1];       // link pairs (l3, l4) (l5, l7) | (l8, ee) self -
-                float coll = ((v0.x + v0.y) + (2.f * v0.z + v0.w)) + (2.f * v1.x + v1.y);
-                coll += (float)(T - 1) * sm.coll_const;
-                coll *= P.sphere_w_coll;
-                const float self = (v1.z + (float)(T - 1) * sm.self_const) * P.self_w_coll;
+                float coll, self = 0.f;
+                if constexpr (NB > 0) {
+                    mbar_wait(bar_res(wa), rc & 1u);
+                    const float4* ba = reinterpret_cast<const float4*>(bacc + (size_t)(wa * 32 + lane) * 8);
+                    const float4 v0 = ba[0], v1 = ba[1];       // link pairs (l3, l4) (l5, l7) | (l8, ee) self -
+                    coll = ((v0.x + v0.y) + (2.f * v0.z + v0.w)) + (2.f * v1.x + v1.y);
+                    coll += (float)(T - 1) * sm.coll_const;
+                    coll *= P.sphere_w_coll;
+                    self = (v1.z + (float)(T - 1) * sm.self_const) * P.self_w_coll;
+                } else {
+                    coll = ((tcm.c_coll + tcm.map_pending) + (float)tcm.map_pending_u8) * P.map_w_coll;     // 0 without a map
+                }
                 // summation order of the shipped cost lists: CostGP (start + gp), CostGoalPrior, self-collision, obstacle
                 // collision, EE goal (examples/panda_environment.py:90), then += IS (planner.py:236)
                 const float c = (((((st + gp) + go) + self) + coll) + ee) + is;
@@ -352,7 +369,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                     wsm[sl] = c;
                     if (last && A.costs) A.costs[(size_t)bp * S + sl] = c;
                 }
-            } else {
+            } else if constexpr (NB > 0) {
                 // ================= link warps =================
                 // per stage: the R state warps this warp serves, in turn; the stage's link-field sums are folded into the
                 // shared-memory accumulators of (state warp, lane) — a fixed order, so results do not depend on timing
@@ -460,8 +477,8 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
         } else {
             const int n_items = T * NP2, nnz = nzo[NCH];
             for (int item = tid; item < n_items; item += BS) {
-                const int t_ = item >> 2, k = item & 3;
-                const bool full = k < 3;
+                const int t_ = item / NP2, k = item - t_ * NP2;
+                const bool full = 2 * k + 1 < N;
                 float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 for (int j = 0; j < nnz; ++j) {
                     const int s = nzl[j];
@@ -509,17 +526,17 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
     for (int k = tid; k < M; k += BS) A.means[(size_t)bp * M + k] = rec[(k / d) * REC + REC_M + 8 + pidx(k % d)];
 }
 
-template <int CHAIN, int NA, int NB>
+template <int N, int CHAIN, int NA, int NB>
 static int launch_split_cfg(const sgpmp_shape_t& sh, const CostParams<float>& P, const IterArgs<float>& A, cudaStream_t st) {
     using Cfg = SplitCfg<NA, NB>;
-    constexpr int d = 14, NSTG = SGPMP_SPLIT_NSTG;
+    constexpr int d = 2 * N, NSTG = SGPMP_SPLIT_NSTG, REC = rec_floats(N);
     const int T = sh.T, M = T * d, Mpad = (M + 3) & ~3, Spad = (sh.S + 3) & ~3, NCH = (sh.S + 31) >> 5;
     const size_t phase_bytes = ((size_t)Mpad + Spad + ((NCH + 4) & ~3)) * 4;
     const size_t uni = phase_bytes > Cfg::pass1_bytes() ? phase_bytes : Cfg::pass1_bytes();
     const size_t smem = ((size_t)SPH_SMEM + (size_t)T * REC + Spad + 32 + 32) * sizeof(float) + 32 * sizeof(double) +
-                        (size_t)((NA * (2 * NSTG + 1) + 1) & ~1) * sizeof(uint64_t) + ((uni + 15) & ~(size_t)15);
+                        (size_t)(NB ? ((NA * (2 * NSTG + 1) + 1) & ~1) : 0) * sizeof(uint64_t) + ((uni + 15) & ~(size_t)15);
     if (smem > 227 * 1024) return SGPMP_ERR_UNSUPPORTED;
-    auto kern = iterate_split_kernel<CHAIN, NA, NB>;
+    auto kern = iterate_split_kernel<N, CHAIN, NA, NB>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned n_cta = (unsigned)(sh.B * sh.G * sh.K);
     kern<<<n_cta, Cfg::BS, smem, st>>>(P, A);
@@ -533,16 +550,38 @@ static int launch_split_chain(const sgpmp_shape_t& sh, const CostParams<float>& 
     // equal numbers of state and link warps measured best at C4 (4,4: 14.55 ms; 4,2: 15.7; 8,4: 15.6; 4,1: 20.4; 6,2: 20.2)
     int na = sh.S > 64 ? 4 : (sh.S > 32 ? 2 : 1), nb = na;
     if (cfg_env) sscanf(cfg_env, "%d,%d", &na, &nb);
-#define SGPMP_SPLIT_CASE(a, b) if (na == a && nb == b) return launch_split_cfg<CHAIN, a, b>(sh, P, A, st);
-    SGPMP_SPLIT_CASE(4, 2) SGPMP_SPLIT_CASE(4, 4) SGPMP_SPLIT_CASE(4, 1) SGPMP_SPLIT_CASE(8, 4) SGPMP_SPLIT_CASE(8, 2)
-    SGPMP_SPLIT_CASE(2, 1) SGPMP_SPLIT_CASE(2, 2) SGPMP_SPLIT_CASE(1, 1) SGPMP_SPLIT_CASE(6, 2)
+#define SGPMP_SPLIT_CASE(a, b) if (na == a && nb == b) return launch_split_cfg<7, CHAIN, a, b>(sh, P, A, st);
+    SGPMP_SPLIT_CASE(4, 4) SGPMP_SPLIT_CASE(2, 2) SGPMP_SPLIT_CASE(1, 1) SGPMP_SPLIT_CASE(4, 2) SGPMP_SPLIT_CASE(8, 4)
 #undef SGPMP_SPLIT_CASE
     set_error("sgpmp_iterate(split): configuration %d,%d is not instantiated", na, nb);
     return SGPMP_ERR_INVALID_ARG;
 }
 
+// state-only form (no link fields): n_dof 2, 3, 4, 6 — the planar occupancy-map cost or no obstacle cost at all
+template <int N>
+static int launch_state_only(const sgpmp_shape_t& sh, const CostParams<float>& P, const IterArgs<float>& A, cudaStream_t st) {
+    static const char* na_env = getenv("SGPMP_STATE_WARPS");      // tuning aid: state warps per CTA (1, 2, 4, 8)
+    int na = sh.S > 64 ? 4 : (sh.S > 32 ? 2 : 1);
+    if (na_env) na = atoi(na_env);
+    if (na == 8) return launch_split_cfg<N, 0, 8, 0>(sh, P, A, st);
+    if (na == 4) return launch_split_cfg<N, 0, 4, 0>(sh, P, A, st);
+    if (na == 2) return launch_split_cfg<N, 0, 2, 0>(sh, P, A, st);
+    return launch_split_cfg<N, 0, 1, 0>(sh, P, A, st);
+}
+
 int launch_iterate_split(const sgpmp_shape_t& sh, const CostParams<float>& P, const IterArgs<float>& A, int chain, cudaStream_t st) {
-    if (sh.n_dof != 7 || sh.T < 2) return SGPMP_ERR_UNSUPPORTED;
+    if (sh.T < 2) return SGPMP_ERR_UNSUPPORTED;
+    if (chain == 0) {
+        if (P.has_spheres || P.has_self || P.has_ee) return SGPMP_ERR_UNSUPPORTED;
+        switch (sh.n_dof) {
+            case 2: return launch_state_only<2>(sh, P, A, st);
+            case 3: return launch_state_only<3>(sh, P, A, st);
+            case 4: return launch_state_only<4>(sh, P, A, st);
+            case 6: return launch_state_only<6>(sh, P, A, st);
+            default: return SGPMP_ERR_UNSUPPORTED;
+        }
+    }
+    if (sh.n_dof != 7) return SGPMP_ERR_UNSUPPORTED;
     return chain == 2 ? launch_split_chain<2>(sh, P, A, st) : launch_split_chain<1>(sh, P, A, st);
 }
 
