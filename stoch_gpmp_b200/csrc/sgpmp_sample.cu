@@ -76,12 +76,11 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sampl
 // into shared memory; only then does one thread per (sample, DoF of the pair) walk the (cheap) recurrence.  In sample_kernel a
 // thread draws AND walks, i.e. T dependent Philox / Box-Muller chains back to back: with 2,048 samples that is a few lone warps
 // (20 us at B = 1).  Same stream, same recurrence expressions: bit-identical output.
-constexpr int SAMPLE_TILE_SB = 64;
-template <typename real>
+// SB (samples per CTA) is chosen by the launcher so that the grid covers the SMs: 64, 32 or 16.
+template <typename real, int SB>
 __global__ void __launch_bounds__(256)
 sample_tiled_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
                     const real* __restrict__ means, RngKey key, real* __restrict__ samples) {
-    constexpr int SB = SAMPLE_TILE_SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* gh = reinterpret_cast<real*>(smem_raw);       // [T][7]
     real* mu_k = gh + (size_t)T * 7;                    // [T][4]  (pos 2k, pos 2k+1, vel 2k, vel 2k+1) mean of this pair
@@ -194,15 +193,23 @@ template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
                          uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false) {
     if (few && !eps_in && !eps_out) {
-        constexpr int SB = SAMPLE_TILE_SB;
         const int n_pairs = (sh.n_dof + 1) / 2;
+        const int NPf = sh.G * sh.K;
+        const long per_block = (long)sh.B * NPf * n_pairs;
+        int SB = 64;                                     // the largest tile that still gives every SM a CTA
+        while (SB > 16 && per_block * ((sh.S + SB - 1) / SB) < 148) SB >>= 1;
         const size_t smem = ((size_t)sh.T * 11 + (size_t)sh.T * 4 * SB) * sizeof(real);
         if (smem <= 200 * 1024 && n_pairs <= 65535 && (sh.S + SB - 1) / SB <= 65535) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            const int NPf = sh.G * sh.K;
             RngKey keyf = make_rng_key(seed, draw);
-            sample_tiled_kernel<real><<<dim3((unsigned)(sh.B * NPf), (unsigned)n_pairs, (unsigned)((sh.S + SB - 1) / SB)), 256, smem, st>>>(
-                NPf, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NPf, (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples);
+            const dim3 grid((unsigned)(sh.B * NPf), (unsigned)n_pairs, (unsigned)((sh.S + SB - 1) / SB));
+#define SGPMP_TILED(SBV)                                                                                                              \
+            do {                                                                                                                      \
+                if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real, SBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                sample_tiled_kernel<real, SBV><<<grid, 256, smem, st>>>(NPf, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NPf,             \
+                                                                       (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples); \
+            } while (0)
+            if (SB == 64) SGPMP_TILED(64); else if (SB == 32) SGPMP_TILED(32); else SGPMP_TILED(16);
+#undef SGPMP_TILED
             SGPMP_CHECK_LAUNCH("sgpmp_sample(tiled)");
             return SGPMP_OK;
         }
