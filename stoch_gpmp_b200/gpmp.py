@@ -24,6 +24,7 @@ from .planner import StochGPMPBatch, print_info, prior_blocks
 class GPMPBatch(StochGPMPBatch):
 
     _batched = True
+    _warm = False
 
     def __init__(self, num_particles_per_goal, traj_len, opt_iters, dt=None, n_dof=None, step_size=1., temperature=1.,
                  start_state=None, multi_goal_states=None, initial_particle_means=None, cost=None,

@@ -28,6 +28,23 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` costs ~5 us per call; the reference's usage pattern (a Python loop of single-iteration
+    optimize() calls) is host-bound, so the switch is skipped when `dev` already is the current device."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if (dev.index is None or dev.index == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _req(t, name, dtype=None, shape=None):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
@@ -143,7 +160,7 @@ def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0,
                    costs=torch.empty(B, NP, S, dtype=dt, device=dev),
                    weights=torch.empty(B, NP, S, dtype=dt, device=dev) if want_weights else None,
                    grad=torch.empty_like(means) if want_grad else None)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.sgpmp_iterate_lowlat(C.byref(shape), C.byref(desc), _ptr(tables), float(step_size), int(n_iters),
                                                 _ptr(eps_in), seed, draw0, _ptr(means), _ptr(out["means_pre"]), _ptr(out["samples"]),
                                                 _ptr(out["costs"]), _ptr(out["weights"]), _ptr(out["grad"]), _stream()),
@@ -158,7 +175,7 @@ def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0,
         weights=torch.empty(B, NP, S, dtype=dt, device=dev) if want_weights else None,
         grad=torch.empty_like(means) if want_grad else None,
     )
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(lib.sgpmp_iterate(C.byref(shape), C.byref(desc), _ptr(tables), float(step_size), int(n_iters),
                                      _ptr(eps_in), seed, draw0, _ptr(means), _ptr(out["means_pre"]), _ptr(out["samples"]),
                                      _ptr(out["costs"]), _ptr(out["weights"]), _ptr(out["grad"]), _stream()),
