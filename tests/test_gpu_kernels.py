@@ -344,6 +344,34 @@ def test_c3_shape_matches_reference(name, dtype, cuda):
     assert it >= 1
 
 
+@pytest.mark.parametrize("name", GOLDEN_C3)
+def test_fused_link_field_term_dominating(name, cuda):
+    """The fused role-split kernel evaluates the joint sin/cos of the link warps with MUFU (sin.approx / cos.approx, |err| <= 2^-20.9).
+    To see that error where it matters, the cost sigmas are set so that the obstacle term IS the cost (GP / start / goal weights
+    ~1e-8 of it): fused fp32 costs against the fp64 oracle on the same inputs, at the north-star's 1e-5, C3 shape."""
+    g = load(name)
+    spec = dict(OP.spec_from_golden(g), cost_sigma_start=1e3, cost_sigma_gp=1e3, sigma_goal_prior=1e4, sigma_coll=1e-3)
+    dtype = torch.float32
+    T, n, G, K, S = spec['T'], spec['n_dof'], spec['G'], spec['K'], spec['S']
+    d = 2 * n
+    tab = _tables(spec, cuda)
+    _, low = _lowered(spec, cuda, dtype)
+    sh = _ops().make_shape(1, G, K, S, T, n, dtype)
+    sp = torch.tensor(spec['spheres'], device=cuda, dtype=dtype).unsqueeze(0)
+    desc = low.desc(spec['temperature'], sp)
+    pre = 'it0_'
+    eps = torch.tensor(to_sminor(eps_ref_to_traj(eps_from_rng_state(g, pre), T, d)), device=cuda, dtype=dtype)
+    mu = torch.tensor(g[pre + 'means_pre'][None], device=cuda, dtype=dtype)
+    out = _ops().iterate(sh, desc, tab, spec['step_size'], 1, mu.clone(), eps_in=eps.unsqueeze(0))
+    r = OP.iterate(spec, mu.cpu().numpy()[0].astype(np.float64), from_sminor(eps.cpu().numpy())[0].astype(np.float64))
+    coll_share = float(np.abs(r['terms']['coll']).max() / np.abs(r['costs'] - r['terms']['is']).max())
+    assert coll_share > 0.99                                     # the obstacle term really is the cost here
+    cost_wo_is = out['costs'].cpu().numpy()[0].astype(np.float64) - r['terms']['is']
+    err = rel(cost_wo_is, r['costs'] - r['terms']['is'])
+    print(name, 'link-field-dominated cost: fused fp32 vs fp64 oracle %.2e' % err)
+    assert err < TOL_F32
+
+
 def U_softmax(costs, tau):
     z = -costs / tau
     z = z - z.max(-1, keepdims=True)
