@@ -19,6 +19,8 @@
 // stream (Philox, Box-Muller) next to an FMA/XU stream (chain, RBF) to pick from.  See DESIGN.md §4.2.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "sgpmp_common.cuh"
 #include "sgpmp_cost.cuh"
 #include "sgpmp_cost_pairs.cuh"
@@ -372,38 +374,47 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
             } else if constexpr (NB > 0) {
                 // ================= link warps =================
                 // per stage: the R state warps this warp serves, in turn; the stage's link-field sums are folded into the
-                // shared-memory accumulators of (state warp, lane) — a fixed order, so results do not depend on timing
-                for (int t0 = 1; t0 < T; t0 += TS) {
-                    const uint32_t stg = sc % NSTG, use = sc / NSTG;
-                    const int tend = min(t0 + TS, T);
+                // shared-memory accumulators of (state warp, lane) — a fixed order, so results do not depend on timing.
+                // The sweep is instantiated for the common sphere counts as compile-time constants (oc = 0: run-time loop).
+                auto link_sweep = [&](auto oc) {
+                    constexpr int OC = decltype(oc)::value;
+                    for (int t0 = 1; t0 < T; t0 += TS) {
+                        const uint32_t stg = sc % NSTG, use = sc / NSTG;
+                        const int tend = min(t0 + TS, T);
 #pragma unroll 1
-                    for (int j = 0; j < R; ++j) {
-                        const int w = wb + j * NB;
-                        mbar_wait(bar_full(w, stg), use & 1u);
-                        const float2* slot = ring + ((size_t)(w * NSTG + stg) * TS) * SLOT + lane;
-                        TrajCostPairs<N, CHAIN> tc;
-                        tc.begin();
+                        for (int j = 0; j < R; ++j) {
+                            const int w = wb + j * NB;
+                            mbar_wait(bar_full(w, stg), use & 1u);
+                            const float2* slot = ring + ((size_t)(w * NSTG + stg) * TS) * SLOT + lane;
+                            TrajCostPairs<N, CHAIN> tc;
+                            tc.begin();
 #pragma unroll 1
-                        for (int t = t0; t < tend; ++t, slot += SLOT) {
-                            F2 xq[NP2];
-                            xq[0] = ld_f2(slot); xq[1] = ld_f2(slot + 32); xq[2] = ld_f2(slot + 64);
-                            xq[3] = f2(0.f, 0.f);
-                            tc.link_fields(P, sm, xq);
+                            for (int t = t0; t < tend; ++t, slot += SLOT) {
+                                F2 xq[NP2];
+                                xq[0] = ld_f2(slot); xq[1] = ld_f2(slot + 32); xq[2] = ld_f2(slot + 64);
+                                xq[3] = f2(0.f, 0.f);
+                                tc.template link_fields<OC>(P, sm, xq);
+                            }
+                            float4* ba = reinterpret_cast<float4*>(bacc + (size_t)(w * 32 + lane) * 8);
+                            float4 v0 = make_float4(lane0(tc.a01), lane1(tc.a01), lane0(tc.a23), lane1(tc.a23));
+                            float4 v1 = make_float4(lane0(tc.a45), lane1(tc.a45), tc.c_self, 0.f);
+                            if (t0 != 1) {
+                                const float4 o0 = ba[0], o1 = ba[1];
+                                v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+                                v1.x += o1.x; v1.y += o1.y; v1.z += o1.z;
+                            }
+                            ba[0] = v0; ba[1] = v1;
+                            mbar_arrive(bar_empty(w, stg));
+                            if (tend == T) mbar_arrive(bar_res(w));      // last stage of the sweep: the sums are complete
                         }
-                        float4* ba = reinterpret_cast<float4*>(bacc + (size_t)(w * 32 + lane) * 8);
-                        float4 v0 = make_float4(lane0(tc.a01), lane1(tc.a01), lane0(tc.a23), lane1(tc.a23));
-                        float4 v1 = make_float4(lane0(tc.a45), lane1(tc.a45), tc.c_self, 0.f);
-                        if (t0 != 1) {
-                            const float4 o0 = ba[0], o1 = ba[1];
-                            v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
-                            v1.x += o1.x; v1.y += o1.y; v1.z += o1.z;
-                        }
-                        ba[0] = v0; ba[1] = v1;
-                        mbar_arrive(bar_empty(w, stg));
-                        if (tend == T) mbar_arrive(bar_res(w));      // last stage of the sweep: the sums are complete
+                        ++sc;
                     }
-                    ++sc;
-                }
+                };
+                const int n_sph = P.has_spheres ? P.n_spheres : -1;
+                if (n_sph == 5) link_sweep(std::integral_constant<int, 5>{});          // examples/panda_environment.py:125-133
+                else if (n_sph == 4) link_sweep(std::integral_constant<int, 4>{});
+                else if (n_sph == 8) link_sweep(std::integral_constant<int, 8>{});
+                else link_sweep(std::integral_constant<int, 0>{});
             }
             ++rc;
         }
