@@ -108,7 +108,8 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
     static_assert((CHAIN == 0) == (NB == 0), "link warps exist exactly when the chain has link fields");
     static_assert(CHAIN == 0 || N == 7, "Panda structure has 7 joints");
     static_assert(NP2 <= 4, "start / goal staging holds up to 8 DoF");
-    constexpr int TS = SGPMP_SPLIT_TS, NSTG = SGPMP_SPLIT_NSTG, UNROLL_A = SGPMP_SPLIT_UNROLL_A;
+    constexpr int TS = NB ? SGPMP_SPLIT_TS : 16;      // state-only form: a 'stage' is just the span of the two-level GP sum
+    constexpr int NSTG = SGPMP_SPLIT_NSTG, UNROLL_A = SGPMP_SPLIT_UNROLL_A;
     constexpr int SLOT = 3 * 32;                                      // float2 per (state warp, step): q pairs 0..2 x 32 lanes
     const int T = A.T, S = A.S, G = A.G, K = A.K;
     const int M = T * d, Mpad = (M + 3) & ~3, Spad = (S + 3) & ~3, NCH = (S + 31) >> 5;
