@@ -231,7 +231,9 @@ def probe_peaks(dev):
 
 def fused_kernel_name(w, n_particles):
     if w["spheres"] is not None and n_particles * 2 > 2 * 148:
-        return "sgpmp::iterate_split_kernel<1,4,4> (state warps + link warps)"
+        return "sgpmp::iterate_split_kernel<7,1,4,4> (state warps + link warps)"
+    if w["spheres"] is None and not w.get("f64") and w["n_dof"] in (2, 3, 4, 6) and n_particles > 148:
+        return "sgpmp::iterate_split_kernel<%d,0,4,0> (state warps only)" % w["n_dof"]
     return "sgpmp::iterate_kernel<%s,2,%d,%d,%d,1>" % ("double" if w.get("f64") else "float", w["n_dof"],
                                                       128 if (w["spheres"] is None and n_particles >= 10 * 148) else 256,
                                                       1 if w["spheres"] is not None else 0)
