@@ -116,6 +116,8 @@ class LoweredCost:
     def __init__(self, composite, B, G, device, dtype):
         self.B, self.G, self.device, self.dtype = B, G, device, dtype
         gp = goal = coll = selfc = ee = None
+        self.custom = []
+        self.composite_fk = composite.FK
         for c in composite.cost_list:
             if isinstance(c, (CostGP, CostGPTrajectory)):
                 if gp is not None:
@@ -144,8 +146,14 @@ class LoweredCost:
                 if coll is not None:
                     raise NotImplementedError("more than one obstacle field in cost_list")
                 coll = c
+            elif callable(c) or hasattr(c, 'eval'):
+                # a user-defined cost (the reference accepts any object with eval(trajs, x_trajs=..., **observation),
+                # cost_functions.py:47-56): it cannot be compiled into the kernels, so the planner runs the separate-kernel
+                # iteration (K2 -> K3 -> K4) and adds this term, evaluated by the user's own torch code on the materialised
+                # samples, to the kernel's costs before the softmax (planner.py: _custom_costs)
+                self.custom.append(c)
             else:
-                raise NotImplementedError("cost object %s cannot be lowered to the CUDA path (no CPU fallback)"
+                raise NotImplementedError("cost object %s cannot be lowered to the CUDA path and is not callable"
                                           % type(c).__name__)
         if gp is None:
             raise NotImplementedError("cost_list needs a CostGP (start + GP factors) or a CostGPTrajectory")
@@ -218,6 +226,19 @@ class LoweredCost:
         self._spheres_src = None
         self._desc_cache = None
         self._ee_key = None
+
+    def custom_costs(self, trajs, **observation):
+        """Sum of the user-defined terms of cost_list, in list order, on trajs [N, T, d] -> [N] (the calling convention of
+        cost_functions.py:47-56: cost(trajs, x_trajs=FK(q) or None, **observation))."""
+        T, d, n = self.T, 2 * self.n_dof, self.n_dof
+        x_trajs = None
+        if self.composite_fk is not None:
+            x_trajs = self.composite_fk(trajs.reshape(-1, d)[:, :n]).reshape(trajs.shape[0], T, -1, 4, 4)
+        total = 0
+        for c in self.custom:
+            f = c if callable(c) else c.eval
+            total = total + f(trajs, x_trajs=x_trajs, **observation)
+        return total
 
     def _need_fk(self, composite, n):
         if not isinstance(composite.FK, SerialChainFK):

@@ -79,7 +79,7 @@ int sample_launch(const sgpmp_shape_t& sh, const double* tables, const void* mea
 int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
                    const void* means, void* costs, cudaStream_t st);
 int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
-                  void* grad, void* weights, int row_chunks, cudaStream_t st);
+                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre = nullptr);
 
 int iterate_stats_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, uint64_t seed,
                          uint32_t draw, const void* means, void* costs, void* stats, cudaStream_t st);

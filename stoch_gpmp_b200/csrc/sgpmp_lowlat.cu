@@ -30,19 +30,13 @@ extern "C" int sgpmp_iterate_lowlat(const sgpmp_shape_t* shape, const sgpmp_cost
     if ((size_t)row_chunks > (M + 31) / 32) row_chunks = (int)((M + 31) / 32);
     for (int it = 0; it < n_iters; ++it) {
         const bool last = (it == n_iters - 1);
-        if (last && means_pre) {
-            if (cudaMemcpyAsync(means_pre, means, BP * M * w, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-                set_error("sgpmp_iterate_lowlat: means_pre copy failed");
-                return SGPMP_ERR_CUDA;
-            }
-        }
         const void* eps = eps_in ? (const char*)eps_in + (size_t)it * BP * M * sh.S * w : nullptr;
         int rc = sample_launch(sh, tables, means, eps, seed, draw0 + (uint32_t)it, samples_ws, st);
         if (rc != SGPMP_OK) return rc;
         rc = cost_st_launch(sh, *desc, tables, samples_ws, means, costs, st);
         if (rc != SGPMP_OK) return rc;
         rc = update_launch(sh, desc->temperature, step_size, costs, samples_ws, means, last ? grad : nullptr, last ? weights : nullptr,
-                           row_chunks, st);
+                           row_chunks, st, last ? means_pre : nullptr);      // the update kernel also writes the pre-update means
         if (rc != SGPMP_OK) return rc;
     }
     return SGPMP_OK;

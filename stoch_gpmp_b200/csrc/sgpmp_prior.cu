@@ -26,12 +26,22 @@ __global__ void prior_factor_kernel(int n_priors, int T, const double* __restric
     int32_t bad = 0;
     double g11 = 0.0, g21 = 0.0, g22 = 0.0;      // G_{t+1}
     double c11 = 0.0, c12 = 0.0, c21 = 0.0, c22 = 0.0;
+    // The blocks of step t - 1 are loaded while step t is factored: the recursion is one dependent chain of ~40 fp64 operations
+    // (two square roots, three divisions) per step, and a just-in-time load would put an L2 round trip in front of every link of it
+    // (T = 1024: 0.69 -> see profiles/r2/c5_sweep.jsonl).
+    double nd11 = D[(T - 1) * 3 + 0], nd12 = D[(T - 1) * 3 + 1], nd22 = D[(T - 1) * 3 + 2];
+    double no11 = 0.0, no12 = 0.0, no21 = 0.0, no22 = 0.0;
     for (int t = T - 1; t >= 0; --t) {
-        const double d11 = D[t * 3 + 0], d12 = D[t * 3 + 1], d22 = D[t * 3 + 2];
+        const double d11 = nd11, d12 = nd12, d22 = nd22;
         double s11 = d11, s12 = d12, s22 = d22;
         double o11 = 0.0, o12 = 0.0, o21 = 0.0, o22 = 0.0;
-        if (t < T - 1) {
-            o11 = O[t * 4 + 0]; o12 = O[t * 4 + 1]; o21 = O[t * 4 + 2]; o22 = O[t * 4 + 3];
+        const bool inner = t < T - 1;
+        if (inner) { o11 = no11; o12 = no12; o21 = no21; o22 = no22; }
+        if (t > 0) {
+            nd11 = D[(t - 1) * 3 + 0]; nd12 = D[(t - 1) * 3 + 1]; nd22 = D[(t - 1) * 3 + 2];
+            no11 = O[(t - 1) * 4 + 0]; no12 = O[(t - 1) * 4 + 1]; no21 = O[(t - 1) * 4 + 2]; no22 = O[(t - 1) * 4 + 3];
+        }
+        if (inner) {
             // C_t = O_t^T G_{t+1}
             c11 = __dadd_rn(__dmul_rn(o11, g11), __dmul_rn(o21, g21));
             c12 = __dmul_rn(o21, g22);

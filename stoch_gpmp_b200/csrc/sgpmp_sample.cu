@@ -71,52 +71,61 @@ sample_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sampl
     }
 }
 
-// Few-samples variant (one planning problem): one CTA per (particle, DoF pair, block of 64 samples).  The normals of all T steps
-// are drawn first, by all 256 threads in parallel over (time step, sample) — the counter-based stream does not care who draws —
-// into shared memory; only then does one thread per (sample, DoF of the pair) walk the (cheap) recurrence.  In sample_kernel a
+// Few-samples variant (one planning problem; C5: long horizons): one CTA per (particle, DoF pair, block of SB samples), time in
+// CHUNKS of TC steps.  Per chunk the normals of all TC steps are drawn first, by all 256 threads in parallel over (time step,
+// sample) — the counter-based stream does not care who draws — into shared memory; only then does one thread per (sample, DoF of
+// the pair) walk the (cheap) recurrence over the chunk, carrying (y_pos, y_vel) to the next chunk in registers.  In sample_kernel a
 // thread draws AND walks, i.e. T dependent Philox / Box-Muller chains back to back: with 2,048 samples that is a few lone warps
-// (20 us at B = 1).  Same stream, same recurrence expressions: bit-identical output.
-// SB (samples per CTA) is chosen by the launcher so that the grid covers the SMs: 64, 32 or 16.
+// (20 us at B = 1, T = 64; 1.37 ms at T = 1024 in fp64).  Same stream, same recurrence expressions: bit-identical output.
+// SB (samples per CTA) is chosen by the launcher so that the grid covers the SMs (64 ... 8), TC so that the chunk fits in
+// shared memory with several CTAs per SM (one CTA's walk then runs under another's draw).
 template <typename real, int SB>
 __global__ void __launch_bounds__(256)
-sample_tiled_kernel(int NP, int S, int T, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
+sample_tiled_kernel(int NP, int S, int T, int TC, int n, int64_t particle_gid0, uint32_t sample_gid0, const double* __restrict__ tab,
                     const real* __restrict__ means, RngKey key, real* __restrict__ samples) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    real* gh = reinterpret_cast<real*>(smem_raw);       // [T][7]
-    real* mu_k = gh + (size_t)T * 7;                    // [T][4]  (pos 2k, pos 2k+1, vel 2k, vel 2k+1) mean of this pair
-    real* eps = mu_k + (size_t)T * 4;                   // [T][4][SB]  same component order
+    real* gh = reinterpret_cast<real*>(smem_raw);       // [TC][7]
+    real* mu_k = gh + (size_t)TC * 7;                   // [TC][4]  (pos 2k, pos 2k+1, vel 2k, vel 2k+1) mean of this pair
+    real* eps = mu_k + (size_t)TC * 4;                  // [TC][4][SB]  same component order
     const int bp = blockIdx.x, k = blockIdx.y, s0 = blockIdx.z * SB;
     const int d = 2 * n, i0 = 2 * k;
     const bool full = (i0 + 1 < n);
-    for (int q = threadIdx.x; q < T * 7; q += blockDim.x)
-        gh[q] = (real)tab[(size_t)(q / 7) * SGPMP_TABLE_STRIDE + (q % 7)];
-    for (int q = threadIdx.x; q < T * 4; q += blockDim.x) {
-        const int t = q >> 2, c = q & 3, h = c & 1, a = c >> 1;
-        mu_k[q] = (h == 0 || full) ? means[(size_t)bp * T * d + (size_t)t * d + a * n + i0 + h] : (real)0;
-    }
     const uint32_t pgid = (uint32_t)(particle_gid0 + bp);
-    for (int item = threadIdx.x; item < T * SB; item += blockDim.x) {
-        const int t = item / SB, sl = item - t * SB, s = s0 + sl;
-        if (s < S) {
-            real p0, p1, v0, v1;
-            normal_pair<real>(key, (uint32_t)t, (uint32_t)k, full, sample_gid0 + (uint32_t)s, pgid, p0, p1, v0, v1);
-            real* e = eps + (size_t)t * 4 * SB + sl;
-            e[0] = p0; e[SB] = p1; e[2 * SB] = v0; e[3 * SB] = v1;
-        }
-    }
-    __syncthreads();
     const int h = threadIdx.x / SB, sl = threadIdx.x - h * SB, s = s0 + sl;
-    if (h >= 2 || s >= S || (h == 1 && !full)) return;
+    const bool walker = !(h >= 2 || s >= S || (h == 1 && !full));
     const size_t base = (size_t)bp * T * d * S;
     real yp = 0, yv = 0;
-    for (int t = 0; t < T; ++t) {
-        const real* r = gh + t * 7;
-        const real e0 = eps[((size_t)t * 4 + h) * SB + sl], e1 = eps[((size_t)t * 4 + 2 + h) * SB + sl];
-        const real np_ = r[0] * e0 - (r[3] * yp + r[4] * yv);
-        const real nv_ = r[1] * e0 + r[2] * e1 - (r[5] * yp + r[6] * yv);
-        yp = np_; yv = nv_;
-        samples[base + ((size_t)t * d + i0 + h) * S + s] = mu_k[4 * t + h] + np_;
-        samples[base + ((size_t)t * d + n + i0 + h) * S + s] = mu_k[4 * t + 2 + h] + nv_;
+    for (int t0 = 0; t0 < T; t0 += TC) {
+        const int tc = min(TC, T - t0);
+        if (t0) __syncthreads();                         // the walkers are done with the previous chunk
+        for (int q = threadIdx.x; q < tc * 7; q += blockDim.x)
+            gh[q] = (real)tab[(size_t)(t0 + q / 7) * SGPMP_TABLE_STRIDE + (q % 7)];
+        for (int q = threadIdx.x; q < tc * 4; q += blockDim.x) {
+            const int t = t0 + (q >> 2), c = q & 3, hh = c & 1, a = c >> 1;
+            mu_k[q] = (hh == 0 || full) ? means[(size_t)bp * T * d + (size_t)t * d + a * n + i0 + hh] : (real)0;
+        }
+        for (int item = threadIdx.x; item < tc * SB; item += blockDim.x) {
+            const int tl = item / SB, isl = item - tl * SB, is = s0 + isl;
+            if (is < S) {
+                real p0, p1, v0, v1;
+                normal_pair<real>(key, (uint32_t)(t0 + tl), (uint32_t)k, full, sample_gid0 + (uint32_t)is, pgid, p0, p1, v0, v1);
+                real* e = eps + (size_t)tl * 4 * SB + isl;
+                e[0] = p0; e[SB] = p1; e[2 * SB] = v0; e[3 * SB] = v1;
+            }
+        }
+        __syncthreads();
+        if (walker) {
+            for (int tl = 0; tl < tc; ++tl) {
+                const real* r = gh + tl * 7;
+                const real e0 = eps[((size_t)tl * 4 + h) * SB + sl], e1 = eps[((size_t)tl * 4 + 2 + h) * SB + sl];
+                const real np_ = r[0] * e0 - (r[3] * yp + r[4] * yv);
+                const real nv_ = r[1] * e0 + r[2] * e1 - (r[5] * yp + r[6] * yv);
+                yp = np_; yv = nv_;
+                const int t = t0 + tl;
+                samples[base + ((size_t)t * d + i0 + h) * S + s] = mu_k[4 * tl + h] + np_;
+                samples[base + ((size_t)t * d + n + i0 + h) * S + s] = mu_k[4 * tl + 2 + h] + nv_;
+            }
+        }
     }
 }
 
@@ -192,23 +201,28 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
 template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
                          uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false) {
-    if (few && !eps_in && !eps_out) {
+    const long n_samples_total = (long)sh.B * sh.G * sh.K * sh.S;
+    if (!eps_in && !eps_out && (few || n_samples_total < 148L * 512)) {
         const int n_pairs = (sh.n_dof + 1) / 2;
         const int NPf = sh.G * sh.K;
         const long per_block = (long)sh.B * NPf * n_pairs;
         int SB = 64;                                     // the largest tile that still gives every SM a CTA
-        while (SB > 16 && per_block * ((sh.S + SB - 1) / SB) < 148) SB >>= 1;
-        const size_t smem = ((size_t)sh.T * 11 + (size_t)sh.T * 4 * SB) * sizeof(real);
-        if (smem <= 200 * 1024 && n_pairs <= 65535 && (sh.S + SB - 1) / SB <= 65535) {
+        while (SB > 8 && per_block * ((sh.S + SB - 1) / SB) < 148) SB >>= 1;
+        const size_t per_step = (size_t)(11 + 4 * SB) * sizeof(real);
+        // the whole horizon as one chunk while that leaves two CTAs per SM, else chunks of <= 40 KB (five CTAs per SM)
+        int TC = sh.T;
+        if ((size_t)sh.T * per_step > 96 * 1024) TC = (int)((40 * 1024) / per_step);
+        const size_t smem = (size_t)TC * per_step;
+        if (TC >= 8 && n_pairs <= 65535 && (sh.S + SB - 1) / SB <= 65535) {
             RngKey keyf = make_rng_key(seed, draw);
             const dim3 grid((unsigned)(sh.B * NPf), (unsigned)n_pairs, (unsigned)((sh.S + SB - 1) / SB));
 #define SGPMP_TILED(SBV)                                                                                                              \
             do {                                                                                                                      \
                 if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real, SBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                sample_tiled_kernel<real, SBV><<<grid, 256, smem, st>>>(NPf, sh.S, sh.T, sh.n_dof, sh.problem_gid0 * NPf,             \
+                sample_tiled_kernel<real, SBV><<<grid, 256, smem, st>>>(NPf, sh.S, sh.T, TC, sh.n_dof, sh.problem_gid0 * NPf,         \
                                                                        (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples); \
             } while (0)
-            if (SB == 64) SGPMP_TILED(64); else if (SB == 32) SGPMP_TILED(32); else SGPMP_TILED(16);
+            if (SB == 64) SGPMP_TILED(64); else if (SB == 32) SGPMP_TILED(32); else if (SB == 16) SGPMP_TILED(16); else SGPMP_TILED(8);
 #undef SGPMP_TILED
             SGPMP_CHECK_LAUNCH("sgpmp_sample(tiled)");
             return SGPMP_OK;
@@ -218,7 +232,6 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
     // machine with one thread each.  Few samples with long horizons (C5: one problem, T up to 1024) are latency-bound on the
     // sequential recurrence, so they take the thread-per-(sample, DoF) kernel below: n times the threads, the same stream
     // (T = 1024, n = 7, fp64, 2,048 samples: 2.69 ms -> see profiles/r1/c5_sweep.jsonl).
-    const long n_samples_total = (long)sh.B * sh.G * sh.K * sh.S;
     if (!eps_in && n_samples_total >= 148L * 512) {
         int rc = SGPMP_ERR_UNSUPPORTED;
         switch (sh.n_dof) {

@@ -65,7 +65,7 @@ __device__ __forceinline__ void block_softmax(const real* __restrict__ c, int S,
 template <typename real>
 __global__ void __launch_bounds__(256)
 update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs, const real* __restrict__ samples,
-              real* __restrict__ means, real* __restrict__ grad, real* __restrict__ weights) {
+              real* __restrict__ means, real* __restrict__ grad, real* __restrict__ weights, real* __restrict__ means_pre) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* wsm = reinterpret_cast<real*>(smem_raw);   // [S]
     real* red = wsm + S;                             // [32]
@@ -98,6 +98,7 @@ update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs,
             const real a = warp_sum(acc[q]);
             if (lane == 0 && r0 + q < row_hi) {
                 if (grad) grad[bp * M + r0 + q] = a;
+                if (means_pre) means_pre[bp * M + r0 + q] = mu[q];        // the means this iteration sampled from (planner.py:252-253)
                 means[bp * M + r0 + q] = mu[q] + step * a;
             }
         }
@@ -174,13 +175,13 @@ __global__ void apply_stats_kernel(int n_particles, int T, int n, const double* 
 
 template <typename real>
 static int launch_update(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples,
-                         void* means, void* grad, void* weights, cudaStream_t st, int row_chunks = 1) {
+                         void* means, void* grad, void* weights, cudaStream_t st, int row_chunks = 1, void* means_pre = nullptr) {
     const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
     const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
     if (smem > 48 * 1024) cudaFuncSetAttribute(update_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     update_kernel<real><<<dim3((unsigned)(sh.B * NP), (unsigned)row_chunks), 256, smem, st>>>(sh.S, M, (real)tau, (real)step, (const real*)costs,
                                                                  (const real*)samples, (real*)means, (real*)grad,
-                                                                 (real*)weights);
+                                                                 (real*)weights, (real*)means_pre);
     SGPMP_CHECK_LAUNCH("sgpmp_update");
     return SGPMP_OK;
 }
@@ -209,9 +210,9 @@ static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, dou
 }
 
 int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
-                  void* grad, void* weights, int row_chunks, cudaStream_t st) {
-    if (sh.dtype == SGPMP_F32) return launch_update<float>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks);
-    return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks);
+                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre) {
+    if (sh.dtype == SGPMP_F32) return launch_update<float>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre);
+    return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre);
 }
 
 int merge_apply_stats_launch(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats_all, int n_ranks,

@@ -61,6 +61,9 @@ class GPMPBatch(StochGPMPBatch):
         low = self._lowered
         if low is None:
             raise NotImplementedError("GPMP needs a CostComposite (cost=...)")
+        if low.custom:
+            raise NotImplementedError("GPMP needs the linear system of every cost term; user-defined cost objects (%s) only work "
+                                      "with StochGPMP" % ", ".join(type(c).__name__ for c in low.custom))
         if not low.sigma_start > 0:
             # the reference's CostGPTrajectory.get_linear_system is `pass` (cost_functions.py:217-218): GPMP fails on it too
             raise NotImplementedError("GPMP cannot take CostGPTrajectory (no linear system in the reference either); use CostGP")

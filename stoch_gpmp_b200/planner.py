@@ -234,7 +234,7 @@ class StochGPMPBatch:
         far-away placeholder sphere when the cost list has a sphere field (same kernel family; the sphere count is a run-time
         loop).  No state of the planner changes.  $SGPMP_WARMUP=0 skips it."""
         import os
-        if (not self._warm or self._lowered is None or os.environ.get("SGPMP_WARMUP") == "0" or
+        if (not self._warm or self._lowered is None or self._lowered.custom or os.environ.get("SGPMP_WARMUP") == "0" or
                 self.num_problems * self.num_particles > 4096):
             return
         try:
@@ -315,9 +315,36 @@ class StochGPMPBatch:
         self._samples_sminor = xs
         self._state_samples = xs.permute(0, 1, 4, 2, 3)
         costs = ops.cost(sh, self._desc(observation), self._tables, xs, self._means)
+        if self._lowered.custom:
+            costs = costs + self._custom_costs(xs, observation)
         ss = self._state_samples
         return (self._out(ss[..., -n:]), self._out(ss[..., :n]),
                 self._out(self._means[..., -n:].clone()), self._out(self._means[..., :n].clone()), self._out(costs))
+
+    def _custom_costs(self, xs, observation):
+        """User-defined terms of cost_list (objects the kernels cannot lower), evaluated by the user's torch code on the
+        materialised samples xs [B,NP,T,d,S] with the reference's calling convention (cost_functions.py:47-56) -> [B,NP,S]."""
+        B, NP, T, d, S = xs.shape
+        trajs = xs.permute(0, 1, 4, 2, 3).reshape(B * NP * S, T, d)
+        c = self._lowered.custom_costs(trajs, **observation)
+        return torch.as_tensor(c, device=self.device).to(self.dtype).reshape(B, NP, S)
+
+    def _optimize_separate(self, opt_iters, observation, _eps=None):
+        """optimize() for cost lists with user-defined terms: the reference-method iteration K2 sample -> K3 cost (+ IS) -> user
+        terms (torch) -> K4 update, with the samples materialised every iteration (the fused kernel never materialises them, so it
+        cannot hand them to Python code).  Same RNG stream and same outputs as ops.iterate()."""
+        sh = self._shape()
+        desc = self._desc(observation)
+        out = None
+        for it in range(opt_iters):
+            eps = None if _eps is None else _eps[it].contiguous()
+            xs = ops.sample(sh, self._tables, self._means, eps_in=eps, seed=self.seed, draw=self._draw)
+            self._draw += 1
+            costs = ops.cost(sh, desc, self._tables, xs, self._means) + self._custom_costs(xs, observation)
+            means_pre = self._means.clone()
+            grad, w = ops.update(sh, self.temperature, self.step_size, costs.contiguous(), xs, self._means)
+            out = dict(means_pre=means_pre, samples=xs, costs=costs, weights=w, grad=grad)
+        return out
 
     def _update_distribution(self, costs, traj_samples=None):
         """planner.py:263-275.  `traj_samples` must be the samples of the last sample_and_eval()."""
@@ -367,9 +394,14 @@ class StochGPMPBatch:
             t_iter = time.time()
             eps = None if _eps is None else _eps[done:done + c].contiguous()
             last_chunk = (done + c == opt_iters)
-            out = ops.iterate(sh, desc, self._tables, self.step_size, c, self._means, eps_in=eps, seed=self.seed,
-                              draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat(c))
-            self._draw += c
+            if self._lowered.custom:
+                out = self._optimize_separate(c, observation, _eps=eps)
+                if not (return_samples and last_chunk):
+                    out['samples'] = None
+            else:
+                out = ops.iterate(sh, desc, self._tables, self.step_size, c, self._means, eps_in=eps, seed=self.seed,
+                                  draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat(c))
+                self._draw += c
             done += c
             if debug:
                 print_info(done - 1, opt_iters, t_iter, start_time, out['costs'])
@@ -413,6 +445,9 @@ class StochGPMPBatch:
         s_loc = self.num_samples // world
         n = self.n_dof
         desc = self._desc(observation)
+        if self._lowered.custom:
+            raise NotImplementedError("split-particle mode runs the fused statistics kernel; user-defined cost objects need the "
+                                      "separate-kernel iteration of optimize()")
         sh_loc = ops.make_shape(self.num_problems, self.num_goals, self.num_particles_per_goal, s_loc, self.traj_len, n,
                                 self.dtype, self.problem_offset, sample_gid0=rank * s_loc)
         comm = parallel.NcclComm.for_group(group, self.device).handle if world > 1 else None

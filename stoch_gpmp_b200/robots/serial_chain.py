@@ -52,6 +52,32 @@ class SerialChainFK:
             if j != (f if f < self.n_dofs else -1):
                 raise NotImplementedError("SerialChainFK: joints must come first and in order (frame %d has joint %d)" % (f, j))
 
+    def __call__(self, q):
+        """Link frames as 4x4 transforms, [..., n_dofs] -> [..., num_links, 4, 4], in torch on q's device: the calling
+        convention of the reference's FK hook (cost_functions.py:51-52).  Only user-defined cost terms go through this (they
+        receive `x_trajs` like in the reference); the CUDA kernels evaluate the chain themselves from the descriptor."""
+        import torch
+        lead = q.shape[:-1]
+        q = q.reshape(-1, q.shape[-1])
+        N = q.shape[0]
+        kw = dict(dtype=q.dtype, device=q.device)
+        H = torch.eye(4, **kw).expand(N, 4, 4)
+        frames = [H] if self.include_base else []
+        for f, j in enumerate(self.joint):
+            F = torch.eye(4, **kw)
+            F[:3, :3] = torch.tensor(self.R[f], **kw).reshape(3, 3)
+            F[:3, 3] = torch.tensor(self.xyz[f], **kw)
+            H = H @ F
+            if j >= 0:
+                c, s_ = torch.cos(q[:, j]), torch.sin(q[:, j])
+                Rz = torch.zeros(N, 4, 4, **kw)
+                Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1] = c, -s_, s_, c
+                Rz[:, 2, 2] = 1.0
+                Rz[:, 3, 3] = 1.0
+                H = H @ Rz
+            frames.append(H)
+        return torch.stack(frames, dim=1).reshape(*lead, len(frames), 4, 4)
+
     @property
     def num_links(self):
         return len(self.joint) + (1 if self.include_base else 0)

@@ -239,3 +239,28 @@ def test_merge_stats_is_logsumexp_merge():
     full = stats(slice(0, 40))
     assert torch.allclose(merged[..., 2:] / merged[..., 1:2], full[..., 2:] / full[..., 1:2], atol=1e-12)
     assert torch.allclose(merged[..., 0], full[..., 0])
+
+
+def test_serial_chain_fk_callable_matches_oracle_and_custom_terms_are_collected():
+    """SerialChainFK.__call__ is the FK hook user-defined cost terms receive x_trajs from (cost_functions.py:51-52 convention):
+    all link frames as 4x4 transforms, equal to oracle/fk.py; callables in cost_list are collected as user terms by lower()."""
+    from oracle import fk as OFK
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP
+    from stoch_gpmp_b200.robots import PandaFK
+    q = np.random.RandomState(3).uniform(-2.5, 2.5, (4, 6, 7))
+    H = PandaFK()(torch.tensor(q)).numpy()
+    assert H.shape == (4, 6, 11, 4, 4)
+    assert np.abs(H - OFK.fk_all_links(q.reshape(-1, 7)).reshape(H.shape)).max() < 1e-14
+    assert PandaFK(include_base=False)(torch.tensor(q[0])).shape == (6, 10, 4, 4)
+    ta = {'device': torch.device('cpu'), 'dtype': torch.float64}
+    gp = CostGP(7, 8, torch.zeros(14), 0.05, dict(sigma_start=1., sigma_gp=1.), ta)
+
+    def term(trajs, x_trajs=None, **obs):
+        return x_trajs[:, :, -1, 2, 3].sum(-1) + obs['bias']
+    low = CostComposite(7, 8, [gp, term], FK=PandaFK()).lower(1, 1, torch.device('cpu'), torch.float64)
+    assert low.custom == [term]
+    trajs = torch.tensor(np.random.RandomState(4).randn(5, 8, 14))
+    want = PandaFK()(trajs[..., :7])[:, :, -1, 2, 3].sum(-1) + 2.0
+    assert torch.allclose(low.custom_costs(trajs, bias=2.0), want)
+    with pytest.raises(NotImplementedError, match="not callable"):
+        CostComposite(7, 8, [gp, object()]).lower(1, 1, torch.device('cpu'), torch.float64)

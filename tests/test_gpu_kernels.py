@@ -188,6 +188,22 @@ def test_sample_inkernel_rng_matches_oracle_stream(dtype, T, n, S, cuda):
     assert rel(from_sminor(x.cpu().numpy()), y) < (1e-12 if dtype == torch.float64 else 2e-6)
 
 
+@pytest.mark.parametrize("dtype,T,n,S,NPg", [(torch.float64, 1024, 7, 512, 4), (torch.float64, 300, 2, 100, 3),
+                                              (torch.float32, 512, 14, 64, 2), (torch.float32, 64, 3, 37, 1),
+                                              (torch.float64, 200, 5, 520, 40)])
+def test_sample_time_chunked_tiles_equal_thread_per_pair(dtype, T, n, S, NPg, cuda):
+    """Few samples / long horizons (C5) take the tiled sampler (parallel draw per time chunk, then the recurrence with the state
+    carried across chunks); with eps_out requested the thread-per-(sample, DoF pair) kernel runs.  Same stream, same
+    expressions: bit-identical samples (ragged S, odd n, chunk counts 1 ... 26, T not a multiple of the chunk)."""
+    spec = dict(T=T, dt=0.02, goals=np.zeros((NPg, 2 * n)), sigma_start_sample=0.05, sigma_gp_sample=0.5, sigma_goal_sample=0.05)
+    tab = _tables(spec, cuda)
+    sh = _ops().make_shape(1, NPg, 1, S, T, n, dtype, problem_gid0=3)
+    mu = torch.randn(1, NPg, T, 2 * n, dtype=dtype, device=cuda)
+    x_pair, _ = _ops().sample(sh, tab, mu, seed=99, draw=2, want_eps=True)
+    x_tile = _ops().sample(sh, tab, mu, seed=99, draw=2)
+    assert torch.equal(x_pair, x_tile)
+
+
 def test_sample_moments_vs_dense_covariance(cuda):
     """Sample covariance of many in-kernel draws against the dense reference covariance P^-1."""
     T, n, S = 6, 1, 200000

@@ -205,13 +205,11 @@ def test_error_behaviour(cuda, lib):
     # non-PD prior -> ValueError (the reference's failure class, mp_priors_multi.py:106)
     with pytest.raises(ValueError, match="positive definite"):
         _planner(g, spec, cuda, torch.float64, sigma_gp_sample=float('nan'))
-    # un-lowerable cost object -> NotImplementedError
-
-    class Custom(Cost):
-        pass
+    # a cost_list entry that is neither a known cost class nor callable -> NotImplementedError (callables are user-defined
+    # terms, test_user_defined_cost_terms)
     ta = dict(device=cuda, dtype=torch.float64)
     comp = CostComposite(2, spec['T'], [CostGP(2, spec['T'], torch.zeros(4, **ta), 0.02, dict(sigma_start=1., sigma_gp=1.), ta),
-                                        Custom(2, spec['T'])])
+                                        object()])
     with pytest.raises(NotImplementedError):
         _planner(g, spec, cuda, torch.float64, cost=comp)
     # CostGoalPrior built for another (K, S): the reference fails in its reshape (cost_functions.py:379)
@@ -223,6 +221,92 @@ def test_error_behaviour(cuda, lib):
         StochGPMP(1, 4, 8, 1, dt=0.1, n_dof=9, start_state=torch.zeros(18, **ta), multi_goal_states=torch.zeros(1, 18, **ta),
                   cost=None, sigma_start_init=1., sigma_start_sample=1., sigma_goal_init=1., sigma_goal_sample=1.,
                   sigma_gp_init=1., sigma_gp_sample=1., tensor_args=ta)
+
+
+class _TorchGoalPrior:
+    """A user-written cost term with the reference's calling convention (cost_functions.py:47-56): the arithmetic of the
+    reference's CostGoalPrior (cost_functions.py:376-388) in plain torch — goal factor on x_{T-1}, one goal per G block."""
+
+    def __init__(self, goals, K, S, sigma):
+        self.goals, self.K, self.S, self.sigma = goals, K, S, sigma
+        self.calls = 0
+
+    def __call__(self, trajs, x_trajs=None, **observation):
+        self.calls += 1
+        G = self.goals.shape[0]
+        x = trajs.reshape(G, self.K * self.S, trajs.shape[-2], trajs.shape[-1])[:, :, -1, :]
+        e = self.goals[:, None, :] - x
+        return ((e * e).sum(-1) / self.sigma ** 2).reshape(-1)
+
+
+class _TorchEEHeight:
+    """A user-written term that needs forward kinematics: squared height error of the last link frame, summed over time
+    (receives x_trajs [N, T, L, 4, 4] like a reference cost, cost_functions.py:51-56)."""
+
+    def eval(self, trajs, x_trajs=None, **observation):
+        z = x_trajs[:, 1:, -1, 2, 3]
+        return 3.0 * ((z - 0.4) ** 2).sum(-1)
+
+
+@pytest.mark.parametrize("name", ['planar_f64', 'panda_soft_f32'])
+def test_user_defined_cost_terms(name, cuda):
+    """The reference accepts any callable in cost_list.  Here such terms run as the user's torch code on materialised samples
+    (K2 -> K3 -> user terms -> K4).  (1) A torch restatement of CostGoalPrior in place of the lowered one gives the reference's
+    golden costs / means (fp64 1e-10).  (2) A term that reads x_trajs shifts the costs by exactly its own values."""
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dtype = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    T, n = spec['T'], spec['n_dof']
+    d = 2 * n
+    ta = dict(device=cuda, dtype=dtype)
+    comp, _ = _lowered(spec, cuda, dtype)
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGoalPrior
+    user_goal = _TorchGoalPrior(torch.tensor(spec['goals'], **ta), spec['K'], spec['S'], spec['sigma_goal_prior'])
+    cl = [user_goal if isinstance(c, CostGoalPrior) else c for c in comp.cost_list]
+    assert any(c is user_goal for c in cl)
+    comp_user = CostComposite(n, T, cl, FK=comp.FK, tensor_args=ta)
+    pl_ref = _planner(g, spec, cuda, dtype)
+    pl_usr = _planner(g, spec, cuda, dtype, cost=comp_user)
+    obs = _obs(spec, cuda, dtype)
+    pre = f'{pre0}it0_'
+    eps = torch.tensor(to_sminor(eps_ref_to_traj(g[pre + 'eps'], T, d)), device=cuda)
+    for pl in (pl_ref, pl_usr):
+        pl.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+    out_ref = pl_ref.optimize(_eps=eps, **obs)
+    out_usr = pl_usr.optimize(_eps=eps, **obs)
+    assert user_goal.calls == 1
+    tol = 1e-5 if f32 else 1e-12
+    assert torch.equal(out_usr[0], out_ref[0])
+    assert rel(out_usr[2].cpu().numpy(), out_ref[2].cpu().numpy()) < (1e-6 if f32 else 1e-13)
+    assert rel(out_usr[4].cpu().numpy(), out_ref[4].cpu().numpy()) < tol
+    if not f32:
+        assert rel(out_usr[4].cpu().numpy(), g[pre + 'costs']) < 1e-10
+        assert rel(pl_usr.particle_means.cpu().numpy(), g[pre + 'means_post']) < 1e-10
+        assert rel(out_usr[5].cpu().numpy(), g[pre + 'grad']) < 1e-9
+    # in-kernel RNG: the separate-kernel path draws the same stream as the fused loop
+    pl_ref.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+    pl_usr.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+    pl_usr._draw = pl_ref._draw
+    k = 1 if f32 else 2
+    a, b = pl_ref.optimize(opt_iters=k, **obs), pl_usr.optimize(opt_iters=k, **obs)
+    assert rel(b[2].cpu().numpy(), a[2].cpu().numpy()) < (2e-5 if f32 else 1e-12)
+    assert rel(b[4].cpu().numpy(), a[4].cpu().numpy()) < (1e-4 if f32 else 1e-10)
+    if comp.FK is not None:
+        comp_fk = CostComposite(n, T, list(comp.cost_list) + [_TorchEEHeight()], FK=comp.FK, tensor_args=ta)
+        pl_fk = _planner(g, spec, cuda, dtype, cost=comp_fk)
+        pl_fk.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+        pl_ref.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+        o_fk, o_rf = pl_fk.optimize(_eps=eps, **obs), pl_ref.optimize(_eps=eps, **obs)
+        x = torch.cat([o_fk[2], o_fk[3]], -1).reshape(-1, T, d)
+        extra = _TorchEEHeight().eval(x, x_trajs=comp.FK(x[..., :n])).reshape(o_rf[4].shape)
+        assert float(extra.abs().max()) > 0
+        # the totals differ by exactly the user term (to the rounding of the fp32 totals themselves)
+        assert float(((o_fk[4] - o_rf[4]) - extra).abs().max()) < (1e-5 if f32 else 1e-12) * float(o_fk[4].abs().max())
+        # GPMP and the split-particle mode need kernels for every term
+        with pytest.raises(NotImplementedError):
+            pl_fk.optimize_split(**obs)
 
 
 # ------------------------------------------------------------------------------- BASELINE.json shapes
