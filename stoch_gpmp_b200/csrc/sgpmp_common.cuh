@@ -21,6 +21,11 @@ void count_launch(int n = 1);
         }                                            \
     } while (0)
 
+// Dynamic shared memory above which a launcher opts in with cudaFuncAttributeMaxDynamicSharedMemorySize.  The 48 KB default
+// limit counts a kernel's STATIC shared memory too, so the threshold leaves room for it (a launch with 47.9 KB dynamic + 256 B
+// static fails with "invalid argument" otherwise); opting in when it was not strictly needed costs nothing.
+#define SGPMP_SMEM_OPTIN (40 * 1024)
+
 #define SGPMP_CHECK_LAUNCH(name)                                                          \
     do {                                                                                  \
         cudaError_t e_ = cudaGetLastError();                                              \
@@ -73,13 +78,34 @@ struct CostParams {
 template <typename real>
 int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostParams<real>& out);
 
+// Programmatic dependent launch (PDL) for the chain of short kernels of the low-latency iteration (sgpmp_lowlat.cu): a kernel
+// launched with the attribute may START while its predecessor in the stream is still running; everything it does before
+// pdl_wait() must therefore touch only data that no kernel of the chain writes (prior tables, cost constants, its own shared
+// memory, the counter-based RNG), and every kernel of the chain executes pdl_wait() — which returns when the predecessor grid has
+// completed and its writes are visible — before its first dependent access, so completion is transitive along the chain.
+// Both instructions are no-ops in a kernel that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // cross-file launchers used by the low-latency iteration (sgpmp_lowlat.cu)
 int sample_launch(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in, uint64_t seed,
-                  uint32_t draw, void* samples, cudaStream_t st);
+                  uint32_t draw, void* samples, cudaStream_t st, bool pdl = false);
 int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
-                   const void* means, void* costs, cudaStream_t st);
+                   const void* means, void* costs, cudaStream_t st, bool pdl = false);
 int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
-                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre = nullptr);
+                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre = nullptr, bool pdl = false);
 
 int iterate_stats_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, uint64_t seed,
                          uint32_t draw, const void* means, void* costs, void* stats, cudaStream_t st);

@@ -132,6 +132,28 @@ int lower_cost_desc(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& d, CostPar
 template int lower_cost_desc<float>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<float>&);
 template int lower_cost_desc<double>(const sgpmp_shape_t&, const sgpmp_cost_desc_t&, CostParams<double>&);
 
+// Asynchronous global -> shared copies (SASS LDGSTS): the sample stream of K3 is staged through a per-THREAD ring.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// Ring depth (time steps in flight per thread) of cost_kernel's sample stream.  A thread walks T steps and needs the 2 n state
+// components of step t before it can do anything with it; loaded just in time (round 1) every step began with a DRAM round trip
+// (ncu, planar: 46 % of the stall samples on the first use of the loaded state, issue port 50 % busy, 0.34 of the HBM stream).
+// With the ring the loads of step t + DEPTH - 1 are issued (LDGSTS, no destination registers) before step t is consumed, so
+// DEPTH - 1 steps of HBM latency are covered per thread; every thread copies and reads ONLY ITS OWN slots (lane-consecutive
+// words: conflict-free), so no barrier or mbarrier is involved — cp.async.wait_group orders a thread's own copies.  (A CTA-wide
+// TMA ring with mbarriers was measured SLOWER than the just-in-time loads: profiles/r2/k3_tma_experiment.txt.)
+#ifdef SGPMP_COST_RING_DEPTH      // tuning aid
+template <int N> struct CostRing { static constexpr int DEPTH = SGPMP_COST_RING_DEPTH; };
+#else
+template <int N> struct CostRing { static constexpr int DEPTH = N <= 4 ? 4 : (N <= 7 ? 3 : 2); };
+#endif
+
 template <typename real, int N, int CHAIN>
 __global__ void __launch_bounds__(128)
 cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int T,
@@ -139,6 +161,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
             real* __restrict__ costs, real* __restrict__ terms, size_t term_stride) {
     constexpr int d = 2 * N;
     constexpr int DP = (d + 3) & ~3;      // padded row length: rows stay 16-byte aligned for LDS.128
+    constexpr int DEPTH = CostRing<N>::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real* sph = reinterpret_cast<real*>(smem_raw);                       // [MAX_SPHERES][8] + coll_const
     real* bvec = sph + SPH_SMEM;                                         // [T][DP]
@@ -146,6 +169,7 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     real* mu = reinterpret_cast<real*>(tabDO + (size_t)T * 7);           // [T][d]
     real* start = mu + (size_t)T * d;                                    // [d]
     real* goal = start + d;                                              // [d]
+    real* ring = goal + d;                                               // [DEPTH][d][128]  per-thread slots
 
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
@@ -178,11 +202,30 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     TrajCost<real, N, CHAIN> tc;
     tc.begin();
     const real* xs = samples + (size_t)bp * T * d * S + s;
+    real* my = ring + threadIdx.x;
+    int wr = 0, rd = 0;                                   // ring slots of the next step to load / to consume
+    auto issue = [&](int t) {
+        real* dst = my + (size_t)wr * d * 128;
+        wr = (wr + 1 == DEPTH) ? 0 : wr + 1;
+        const real* src = xs + (size_t)t * d * S;
+#pragma unroll
+        for (int j = 0; j < d; ++j) cp_async<sizeof(real)>(dst + j * 128, src + (size_t)j * S);
+    };
+#pragma unroll
+    for (int k = 0; k < DEPTH - 1; ++k) {
+        if (k < T) issue(k);
+        cp_async_commit();
+    }
     for (int t = 0; t < T; ++t) {
+        if (t + DEPTH - 1 < T) issue(t + DEPTH - 1);      // into the slot step t - 1 was read from
+        cp_async_commit();                                // (an empty group near the end keeps the group count uniform)
+        cp_async_wait<DEPTH - 1>();                       // the group of step t has landed
+        const real* slot = my + (size_t)rd * d * 128;
+        rd = (rd + 1 == DEPTH) ? 0 : rd + 1;
         real x[d], y[d];
 #pragma unroll
         for (int j = 0; j < d; ++j) {
-            x[j] = xs[((size_t)t * d + j) * S];
+            x[j] = slot[j * 128];
             y[j] = means ? x[j] - mu[t * d + j] : x[j];
         }
         tc.step(P, sm, t, T, x, y, y + N, means ? bvec + t * DP : nullptr);
@@ -223,10 +266,13 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
     real* part = goal + d;                                               // [NSL][SL], NSL = 32 TW / SL time slices
     const int NP = G * K;
     const int bp = blockIdx.x, b = bp / NP, p = bp - b * NP;
+    pdl_launch_dependents();
     for (int k = threadIdx.x; k < T * 7; k += blockDim.x)
         tabDO[k] = tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + SGPMP_TAB_D11 + (k % 7)];
-    for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
     stage_cta_constants<real, N, CHAIN>(P, b, p / K, G, start, goal, sph);
+    pdl_wait();        // the tables and cost constants above are written by no kernel of the chain; means and samples are
+    for (int k = threadIdx.x; k < T * d; k += blockDim.x) mu[k] = means[(size_t)bp * T * d + k];
+    __syncthreads();
     double mub_part = 0.0;
     for (int k = threadIdx.x; k < T * N; k += blockDim.x) {
         const int t = k / N, i = k - t * N;
@@ -281,44 +327,44 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
 
 template <typename real, int N, int CHAIN, int SL>
 static int launch_cost_st_sl(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
-                             const void* means, void* costs, cudaStream_t st) {
+                             const void* means, void* costs, cudaStream_t st, bool pdl) {
     constexpr int TW = 16;                // 512 threads: SL samples x (512 / SL) time slices
     const int NP = sh.G * sh.K, d = 2 * N;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + SL - 1) / SL));
     const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM + 32 * TW) * sizeof(real);
-    if (smem > 48 * 1024) {
+    if (smem > SGPMP_SMEM_OPTIN) {
         if (smem > 227 * 1024) { set_error("sgpmp_iterate_lowlat: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
         cudaFuncSetAttribute(cost_st_kernel<real, N, CHAIN, TW, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    cost_st_kernel<real, N, CHAIN, TW, SL><<<grid, 32 * TW, smem, st>>>(P, sh.G, sh.K, sh.S, sh.T, tables, (const real*)samples,
-                                                                      (const real*)means, (real*)costs);
+    launch_kernel(cost_st_kernel<real, N, CHAIN, TW, SL>, grid, dim3(32 * TW), smem, st, pdl, P, sh.G, sh.K, sh.S, sh.T, tables,
+                  (const real*)samples, (const real*)means, (real*)costs);
     SGPMP_CHECK_LAUNCH("sgpmp_iterate_lowlat(cost)");
     return SGPMP_OK;
 }
 
 template <typename real, int N, int CHAIN>
 static int launch_cost_st_n(const sgpmp_shape_t& sh, const CostParams<real>& P, const double* tables, const void* samples,
-                            const void* means, void* costs, cudaStream_t st) {
+                            const void* means, void* costs, cudaStream_t st, bool pdl) {
     // 16 samples x 32 time slices per CTA while that still fits one wave of CTAs (one Panda problem: 128 CTAs, 12.8 us against
     // 17.2 us); 32 samples x 16 slices beyond (two problems: 37.9 against 41.6 us per iteration)
     const long ctas16 = (long)sh.B * sh.G * sh.K * ((sh.S + 15) / 16);
-    if (ctas16 <= 148) return launch_cost_st_sl<real, N, CHAIN, 16>(sh, P, tables, samples, means, costs, st);
-    return launch_cost_st_sl<real, N, CHAIN, 32>(sh, P, tables, samples, means, costs, st);
+    if (ctas16 <= 148) return launch_cost_st_sl<real, N, CHAIN, 16>(sh, P, tables, samples, means, costs, st, pdl);
+    return launch_cost_st_sl<real, N, CHAIN, 32>(sh, P, tables, samples, means, costs, st, pdl);
 }
 
 template <typename real>
 static int launch_cost_st(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
-                          const void* means, void* costs, cudaStream_t st) {
+                          const void* means, void* costs, cudaStream_t st, bool pdl) {
     CostParams<real> P;
     int rc = lower_cost_desc<real>(sh, desc, P);
     if (rc != SGPMP_OK) return rc;
     if constexpr (sizeof(real) == 4) {
         if (structured_fields_ok(P) && chain_is_panda_structure(desc, sh.n_dof))
-            return P.has_self ? launch_cost_st_n<real, 7, 2>(sh, P, tables, samples, means, costs, st)
-                              : launch_cost_st_n<real, 7, 1>(sh, P, tables, samples, means, costs, st);
+            return P.has_self ? launch_cost_st_n<real, 7, 2>(sh, P, tables, samples, means, costs, st, pdl)
+                              : launch_cost_st_n<real, 7, 1>(sh, P, tables, samples, means, costs, st, pdl);
     }
     switch (sh.n_dof) {
-#define SGPMP_DOF_CASE(N) case N: return launch_cost_st_n<real, N, 0>(sh, P, tables, samples, means, costs, st);
+#define SGPMP_DOF_CASE(N) case N: return launch_cost_st_n<real, N, 0>(sh, P, tables, samples, means, costs, st, pdl);
 #include "sgpmp_dof_list.inc"
 #undef SGPMP_DOF_CASE
         default:
@@ -328,9 +374,9 @@ static int launch_cost_st(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
 }
 
 int cost_st_launch(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, const double* tables, const void* samples,
-                   const void* means, void* costs, cudaStream_t st) {
-    if (sh.dtype == SGPMP_F32) return launch_cost_st<float>(sh, desc, tables, samples, means, costs, st);
-    return launch_cost_st<double>(sh, desc, tables, samples, means, costs, st);
+                   const void* means, void* costs, cudaStream_t st, bool pdl) {
+    if (sh.dtype == SGPMP_F32) return launch_cost_st<float>(sh, desc, tables, samples, means, costs, st, pdl);
+    return launch_cost_st<double>(sh, desc, tables, samples, means, costs, st, pdl);
 }
 
 // Link-frame origins of N_cfg configurations: q [n_cfg][N] -> pos [n_cfg][L][3].  Same FK code as the cost
@@ -385,8 +431,9 @@ static int launch_cost_n(const sgpmp_shape_t& sh, const CostParams<real>& P, con
                          const void* means, void* costs, void* terms, cudaStream_t st) {
     const int NP = sh.G * sh.K, d = 2 * N, bs = 128;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
-    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM) * sizeof(real);
-    if (smem > 48 * 1024) {
+    const size_t smem = (size_t)sh.T * 7 * sizeof(double) + ((size_t)sh.T * (d + ((d + 3) & ~3)) + 2 * d + SPH_SMEM +
+                                                              (size_t)CostRing<N>::DEPTH * d * bs) * sizeof(real);
+    if (smem > SGPMP_SMEM_OPTIN) {
         if (smem > 227 * 1024) { set_error("sgpmp_cost: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
         cudaFuncSetAttribute(cost_kernel<real, N, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }

@@ -480,7 +480,7 @@ static int launch_gpmp_n(const sgpmp_shape_t& sh, const CostParams<double>& P, G
         const int BP = sh.B * sh.G * sh.K;
         const size_t smem = ((size_t)sh.T * d + 4 * SGPMP_MAX_SPHERES + 2 * d) * sizeof(double);
         if (smem > 227 * 1024) { set_error("sgpmp_gpmp_step: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
-        if (smem > 48 * 1024) cudaFuncSetAttribute(gpmp_assemble_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(gpmp_assemble_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         constexpr int WPB = (d <= 16) ? 4 : 1;       // static shared memory: WPB * (2 d (d+1) + 2 d) doubles
         for (int it = 0; it < n_iters; ++it) {
             // one thread per time step: no more threads than steps (T = 64: 64-thread CTAs, twice the resident CTAs per SM)

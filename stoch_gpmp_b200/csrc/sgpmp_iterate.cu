@@ -413,7 +413,7 @@ static int launch_iterate_nb(const sgpmp_shape_t& sh, const CostParams<real>& P,
         return SGPMP_ERR_UNSUPPORTED;
     }
     auto kern = iterate_kernel<real, PACK, N, BS, CHAIN, CL>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned n_cta = (unsigned)(sh.B * sh.G * sh.K) * CL;
     if constexpr (CL > 1) {
         cudaLaunchConfig_t cfg = {};

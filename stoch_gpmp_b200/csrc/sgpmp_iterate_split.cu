@@ -549,7 +549,7 @@ static int launch_split_cfg(const sgpmp_shape_t& sh, const CostParams<float>& P,
                         (size_t)(NB ? ((NA * (2 * NSTG + 1) + 1) & ~1) : 0) * sizeof(uint64_t) + ((uni + 15) & ~(size_t)15);
     if (smem > 227 * 1024) return SGPMP_ERR_UNSUPPORTED;
     auto kern = iterate_split_kernel<N, CHAIN, NA, NB>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned n_cta = (unsigned)(sh.B * sh.G * sh.K);
     kern<<<n_cta, Cfg::BS, smem, st>>>(P, A);
     SGPMP_CHECK_LAUNCH("sgpmp_iterate(split)");

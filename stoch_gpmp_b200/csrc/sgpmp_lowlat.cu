@@ -8,6 +8,8 @@
 //   K3' cost_st_kernel      thread per (sample, time slice): 16 warps share a trajectory's time steps (sgpmp_cost.cu)
 //   K4  update_kernel       state rows of a particle divided over CTAs (sgpmp_update.cu)
 // all n_iters iterations are enqueued by ONE call from C (a Python-side loop would pay ~15 us of ctypes per launch).
+#include <stdlib.h>
+
 #include "sgpmp_common.cuh"
 
 using namespace sgpmp;
@@ -28,15 +30,21 @@ extern "C" int sgpmp_iterate_lowlat(const sgpmp_shape_t* shape, const sgpmp_cost
     int row_chunks = (int)((2 * 148 + BP - 1) / BP);
     row_chunks = row_chunks < 1 ? 1 : row_chunks;
     if ((size_t)row_chunks > (M + 31) / 32) row_chunks = (int)((M + 31) / 32);
+    // Programmatic dependent launch along the chain K2 -> K3' -> K4 -> K2 ...: each kernel is allowed to start while its predecessor
+    // drains, does what depends on no other kernel (table staging, cost constants, K2's whole Philox / Box-Muller draw) and only then
+    // waits for the predecessor's completion (pdl_wait, sgpmp_common.cuh).  The FIRST kernel of a call is launched normally: what
+    // precedes it in the stream is the caller's (e.g. a torch kernel that wrote the obstacle spheres).  $SGPMP_PDL=0 disables it.
+    static const char* pdl_env = getenv("SGPMP_PDL");
+    const bool pdl = !(pdl_env && pdl_env[0] == '0');
     for (int it = 0; it < n_iters; ++it) {
         const bool last = (it == n_iters - 1);
         const void* eps = eps_in ? (const char*)eps_in + (size_t)it * BP * M * sh.S * w : nullptr;
-        int rc = sample_launch(sh, tables, means, eps, seed, draw0 + (uint32_t)it, samples_ws, st);
+        int rc = sample_launch(sh, tables, means, eps, seed, draw0 + (uint32_t)it, samples_ws, st, pdl && it > 0);
         if (rc != SGPMP_OK) return rc;
-        rc = cost_st_launch(sh, *desc, tables, samples_ws, means, costs, st);
+        rc = cost_st_launch(sh, *desc, tables, samples_ws, means, costs, st, pdl);
         if (rc != SGPMP_OK) return rc;
         rc = update_launch(sh, desc->temperature, step_size, costs, samples_ws, means, last ? grad : nullptr, last ? weights : nullptr,
-                           row_chunks, st, last ? means_pre : nullptr);      // the update kernel also writes the pre-update means
+                           row_chunks, st, last ? means_pre : nullptr, pdl);      // the update kernel also writes the pre-update means
         if (rc != SGPMP_OK) return rc;
     }
     return SGPMP_OK;

@@ -95,15 +95,12 @@ sample_tiled_kernel(int NP, int S, int T, int TC, int n, int64_t particle_gid0, 
     const bool walker = !(h >= 2 || s >= S || (h == 1 && !full));
     const size_t base = (size_t)bp * T * d * S;
     real yp = 0, yv = 0;
+    pdl_launch_dependents();
     for (int t0 = 0; t0 < T; t0 += TC) {
         const int tc = min(TC, T - t0);
         if (t0) __syncthreads();                         // the walkers are done with the previous chunk
         for (int q = threadIdx.x; q < tc * 7; q += blockDim.x)
             gh[q] = (real)tab[(size_t)(t0 + q / 7) * SGPMP_TABLE_STRIDE + (q % 7)];
-        for (int q = threadIdx.x; q < tc * 4; q += blockDim.x) {
-            const int t = t0 + (q >> 2), c = q & 3, hh = c & 1, a = c >> 1;
-            mu_k[q] = (hh == 0 || full) ? means[(size_t)bp * T * d + (size_t)t * d + a * n + i0 + hh] : (real)0;
-        }
         for (int item = threadIdx.x; item < tc * SB; item += blockDim.x) {
             const int tl = item / SB, isl = item - tl * SB, is = s0 + isl;
             if (is < S) {
@@ -112,6 +109,13 @@ sample_tiled_kernel(int NP, int S, int T, int TC, int n, int64_t particle_gid0, 
                 real* e = eps + (size_t)tl * 4 * SB + isl;
                 e[0] = p0; e[SB] = p1; e[2 * SB] = v0; e[3 * SB] = v1;
             }
+        }
+        // PDL: the tables and the draw above depend on no other kernel; the means (written by the previous iteration's update)
+        // and the sample buffer (read by it) do — the first chunk's draw runs under the tail of the predecessor
+        if (t0 == 0) pdl_wait();
+        for (int q = threadIdx.x; q < tc * 4; q += blockDim.x) {
+            const int t = t0 + (q >> 2), c = q & 3, hh = c & 1, a = c >> 1;
+            mu_k[q] = (hh == 0 || full) ? means[(size_t)bp * T * d + (size_t)t * d + a * n + i0 + hh] : (real)0;
         }
         __syncthreads();
         if (walker) {
@@ -187,7 +191,7 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
     const int NP = sh.G * sh.K, bs = 128;
     dim3 grid((unsigned)(sh.B * NP), (unsigned)((sh.S + bs - 1) / bs));
     const size_t smem = (size_t)sh.T * (8 + 2 * N) * sizeof(real);
-    if (smem > 48 * 1024) {
+    if (smem > SGPMP_SMEM_OPTIN) {
         if (smem > 227 * 1024) return SGPMP_ERR_UNSUPPORTED;      // caller falls back to the generic kernel
         cudaFuncSetAttribute(sample_rng_kernel<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
@@ -200,7 +204,8 @@ static int launch_sample_rng(const sgpmp_shape_t& sh, const double* tables, cons
 
 template <typename real>
 static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in,
-                         uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false) {
+                         uint64_t seed, uint32_t draw, void* samples, void* eps_out, cudaStream_t st, bool few = false,
+                         bool pdl = false) {
     const long n_samples_total = (long)sh.B * sh.G * sh.K * sh.S;
     if (!eps_in && !eps_out && (few || n_samples_total < 148L * 512)) {
         const int n_pairs = (sh.n_dof + 1) / 2;
@@ -218,9 +223,9 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
             const dim3 grid((unsigned)(sh.B * NPf), (unsigned)n_pairs, (unsigned)((sh.S + SB - 1) / SB));
 #define SGPMP_TILED(SBV)                                                                                                              \
             do {                                                                                                                      \
-                if (smem > 48 * 1024) cudaFuncSetAttribute(sample_tiled_kernel<real, SBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                sample_tiled_kernel<real, SBV><<<grid, 256, smem, st>>>(NPf, sh.S, sh.T, TC, sh.n_dof, sh.problem_gid0 * NPf,         \
-                                                                       (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples); \
+                if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(sample_tiled_kernel<real, SBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                launch_kernel(sample_tiled_kernel<real, SBV>, grid, dim3(256), smem, st, pdl, NPf, sh.S, sh.T, TC, sh.n_dof,          \
+                              (int64_t)sh.problem_gid0 * NPf, (uint32_t)sh.sample_gid0, tables, (const real*)means, keyf, (real*)samples); \
             } while (0)
             if (SB == 64) SGPMP_TILED(64); else if (SB == 32) SGPMP_TILED(32); else if (SB == 16) SGPMP_TILED(16); else SGPMP_TILED(8);
 #undef SGPMP_TILED
@@ -249,7 +254,7 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
     const size_t mu_bytes = (size_t)sh.T * 2 * sh.n_dof * sizeof(real);
     const int mu_in_smem = (smem + mu_bytes <= 40 * 1024) ? 1 : 0;
     if (mu_in_smem) smem += mu_bytes;
-    if (smem > 48 * 1024) {
+    if (smem > SGPMP_SMEM_OPTIN) {
         if (smem > 227 * 1024) { set_error("sgpmp_sample: T=%d too large for the shared-memory tables", sh.T); return SGPMP_ERR_UNSUPPORTED; }
         cudaFuncSetAttribute(sample_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
@@ -262,10 +267,10 @@ static int launch_sample(const sgpmp_shape_t& sh, const double* tables, const vo
 }
 
 int sample_launch(const sgpmp_shape_t& sh, const double* tables, const void* means, const void* eps_in, uint64_t seed,
-                  uint32_t draw, void* samples, cudaStream_t st) {
+                  uint32_t draw, void* samples, cudaStream_t st, bool pdl) {
     // called by the low-latency iteration only: few samples, so the tiled kernel (parallel draw, then the recurrence)
-    if (sh.dtype == SGPMP_F32) return launch_sample<float>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true);
-    return launch_sample<double>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true);
+    if (sh.dtype == SGPMP_F32) return launch_sample<float>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true, pdl);
+    return launch_sample<double>(sh, tables, means, eps_in, seed, draw, samples, nullptr, st, true, pdl);
 }
 
 }  // namespace sgpmp

@@ -71,6 +71,8 @@ update_kernel(int S, int M, real tau, real step, const real* __restrict__ costs,
     real* red = wsm + S;                             // [32]
     const size_t bp = blockIdx.x;
     real m, Z;
+    pdl_launch_dependents();
+    pdl_wait();                  // everything below reads what the cost kernel wrote
     block_softmax<real>(costs + bp * S, S, tau, wsm, red, true, &m, &Z);
     if (weights && blockIdx.y == 0)
         for (int s = threadIdx.x; s < S; s += blockDim.x) weights[bp * S + s] = wsm[s];
@@ -175,13 +177,13 @@ __global__ void apply_stats_kernel(int n_particles, int T, int n, const double* 
 
 template <typename real>
 static int launch_update(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples,
-                         void* means, void* grad, void* weights, cudaStream_t st, int row_chunks = 1, void* means_pre = nullptr) {
+                         void* means, void* grad, void* weights, cudaStream_t st, int row_chunks = 1, void* means_pre = nullptr,
+                         bool pdl = false) {
     const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
     const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(update_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    update_kernel<real><<<dim3((unsigned)(sh.B * NP), (unsigned)row_chunks), 256, smem, st>>>(sh.S, M, (real)tau, (real)step, (const real*)costs,
-                                                                 (const real*)samples, (real*)means, (real*)grad,
-                                                                 (real*)weights, (real*)means_pre);
+    if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(update_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_kernel(update_kernel<real>, dim3((unsigned)(sh.B * NP), (unsigned)row_chunks), dim3(256), smem, st, pdl, sh.S, M, (real)tau,
+                  (real)step, (const real*)costs, (const real*)samples, (real*)means, (real*)grad, (real*)weights, (real*)means_pre);
     SGPMP_CHECK_LAUNCH("sgpmp_update");
     return SGPMP_OK;
 }
@@ -191,7 +193,7 @@ static int launch_local_stats(const sgpmp_shape_t& sh, double tau, const void* c
                               cudaStream_t st) {
     const int NP = sh.G * sh.K, M = sh.T * 2 * sh.n_dof;
     const size_t smem = ((size_t)sh.S + 32) * sizeof(real);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(local_stats_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > SGPMP_SMEM_OPTIN) cudaFuncSetAttribute(local_stats_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     local_stats_kernel<real><<<(unsigned)(sh.B * NP), 256, smem, st>>>(sh.S, M, (real)tau, (const real*)costs,
                                                                       (const real*)eps, (real*)stats);
     SGPMP_CHECK_LAUNCH("sgpmp_local_stats");
@@ -210,9 +212,9 @@ static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, dou
 }
 
 int update_launch(const sgpmp_shape_t& sh, double tau, double step, const void* costs, const void* samples, void* means,
-                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre) {
-    if (sh.dtype == SGPMP_F32) return launch_update<float>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre);
-    return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre);
+                  void* grad, void* weights, int row_chunks, cudaStream_t st, void* means_pre, bool pdl) {
+    if (sh.dtype == SGPMP_F32) return launch_update<float>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre, pdl);
+    return launch_update<double>(sh, tau, step, costs, samples, means, grad, weights, st, row_chunks, means_pre, pdl);
 }
 
 int merge_apply_stats_launch(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats_all, int n_ranks,
