@@ -561,9 +561,15 @@ static int launch_split_chain(const sgpmp_shape_t& sh, const CostParams<float>& 
     static const char* cfg_env = getenv("SGPMP_SPLIT_CFG");       // tuning aid: "NA,NB"
     // equal numbers of state and link warps measured best at C4 (4,4: 14.55 ms; 4,2: 15.7; 8,4: 15.6; 4,1: 20.4; 6,2: 20.2)
     int na = sh.S > 64 ? 4 : (sh.S > 32 ? 2 : 1), nb = na;
+    // Mid-size batches (the 4096-problem config sharded over 8 GPUs: 2,048 CTAs): 512-thread CTAs, two per SM.  The same 32 warps
+    // per SM, but a CTA takes half as long, so the partial last wave costs half as much (ms per iteration, (4,4) -> (8,8):
+    // 128 problems 0.529 -> 0.502, 256: 0.920 -> 0.861, 512: 1.721 -> 1.699, 1024: 3.417 -> 3.370; 4096: 13.25 -> 13.32, where
+    // the finer interleave of four CTAs' block phases wins instead).
+    const long n_cta = (long)sh.B * sh.G * sh.K;
+    if (sh.S >= 256 && n_cta <= 6144) na = nb = 8;
     if (cfg_env) sscanf(cfg_env, "%d,%d", &na, &nb);
 #define SGPMP_SPLIT_CASE(a, b) if (na == a && nb == b) return launch_split_cfg<7, CHAIN, a, b>(sh, P, A, st);
-    SGPMP_SPLIT_CASE(4, 4) SGPMP_SPLIT_CASE(2, 2) SGPMP_SPLIT_CASE(1, 1) SGPMP_SPLIT_CASE(4, 2) SGPMP_SPLIT_CASE(8, 4)
+    SGPMP_SPLIT_CASE(4, 4) SGPMP_SPLIT_CASE(2, 2) SGPMP_SPLIT_CASE(1, 1) SGPMP_SPLIT_CASE(4, 2) SGPMP_SPLIT_CASE(8, 4) SGPMP_SPLIT_CASE(8, 8)
 #undef SGPMP_SPLIT_CASE
     set_error("sgpmp_iterate(split): configuration %d,%d is not instantiated", na, nb);
     return SGPMP_ERR_INVALID_ARG;
