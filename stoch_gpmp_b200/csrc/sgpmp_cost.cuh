@@ -197,6 +197,21 @@ __device__ __noinline__ real ee_se3_cost(const CostParams<real>& P, const real* 
 // remaining translations point, so q[6] is never needed.
 constexpr int PANDA_EVAL_LINKS = 6;   // link3, link4, link5(=link6), link7, link8(=hand), ee
 
+// Joint sin/cos of the STRUCTURED Panda chain (fp32 scalar paths: standalone K3, the low-latency cost kernel, the single-role
+// fused kernel).  1 (default): MUFU sin.approx / cos.approx, as the link warps of the role-split kernel do (sgpmp_cost_pairs.cuh) —
+// these kernels are FMA-pipe bound with an idle XU pipe, and the polynomials are ~21 FMA-pipe instructions per angle; |err| <=
+// 2^-20.9 displaces a link origin by < 5e-7 m (obstacle-dominated costs move by 3e-6 against the fp64 oracle, inside the 1e-5 bar).
+// 0: the polynomial forms of sgpmp_vec.cuh.  The packed (F2) and fp64 instantiations keep vsincos.
+#ifndef SGPMP_FK_MUFU_SINCOS
+#define SGPMP_FK_MUFU_SINCOS 1
+#endif
+template <typename V>
+__device__ __forceinline__ void fk_sincos(V x, V* s, V* c) { vsincos(x, s, c); }
+#if SGPMP_FK_MUFU_SINCOS
+template <>
+__device__ __forceinline__ void fk_sincos<float>(float x, float* s, float* c) { *s = __sinf(x); *c = __cosf(x); }
+#endif
+
 template <typename V>
 struct Cols {   // rotation columns a, b, c
     V ax, ay, az, bx, by, bz, cx, cy, cz;
@@ -212,7 +227,7 @@ struct Cols {   // rotation columns a, b, c
     }
     __device__ __forceinline__ void rot_z(V q) {  // R <- R Rz(q): a' = c a + s b, b' = c b - s a
         V s, c;
-        vsincos(q, &s, &c);
+        fk_sincos<V>(q, &s, &c);
         rot_z_sc(s, c);
     }
     __device__ __forceinline__ void rot_z_sc(V s, V c) {
@@ -231,8 +246,8 @@ __device__ __forceinline__ void fk_panda_origins(const CostParams<typename VT<V>
     // joints 1 and 2 by hand (R starts as the identity; frame 0: t = (0,0,d1); frame 1: t = 0, Rx(-90)):
     //   a = (c1 c0, c1 s0, -s1), b = (-s1 c0, -s1 s0, -c1), c = (-s0, c0, 0),  p = (0, 0, d1)
     V s0, c0, s1, c1;
-    vsincos(q[0], &s0, &c0);
-    vsincos(q[1], &s1, &c1);
+    fk_sincos<V>(q[0], &s0, &c0);
+    fk_sincos<V>(q[1], &s1, &c1);
     const real d1 = P.p[0][2], t2y = P.p[2][1];
     const V s1c0 = s1 * c0, s1s0 = s1 * s0;
     V px = vfma(-t2y, s1c0, -o3[0]), py = vfma(-t2y, s1s0, -o3[1]), pz = vfma(-t2y, c1, d1 - o3[2]);          // frame 2: p += t2y * b

@@ -40,7 +40,10 @@
 #define SGPMP_SPLIT_UNROLL_A 1  // unroll factor of the state warps' step loop
 #endif
 #ifndef SGPMP_SPLIT_SLEEP_NS
-#define SGPMP_SPLIT_SLEEP_NS 64 // back-off of a warp that finds its mbarrier phase incomplete
+#define SGPMP_SPLIT_SLEEP_NS 64 // back-off of a warp that finds its mbarrier phase incomplete (form without the suspend-time hint)
+#endif
+#ifndef SGPMP_SPLIT_WAIT_HINT_NS
+#define SGPMP_SPLIT_WAIT_HINT_NS 1000   // suspend-time hint of mbarrier.try_wait; 0 selects the try_wait + nanosleep form
 #endif
 
 namespace sgpmp {
@@ -53,9 +56,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Wait until the phase of the given parity has completed (a fresh barrier has "completed" parity 1).  A warp that has to
-// wait SLEEPS between polls: a spinning warp would spend the issue slots the other role needs (first version: 7 % of all
-// executed instructions were this loop).
+// wait is SUSPENDED (try_wait with a suspend-time hint, or nanosleep between polls): a spinning warp would spend the issue
+// slots the other role needs (first version: 7 % of all executed instructions were this loop).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if SGPMP_SPLIT_WAIT_HINT_NS > 0
+    // the hardware suspends the warp inside try_wait for up to the hinted time: no instructions between polls.  Measured at C4
+    // (profiles/r2/wait_variants.txt): hint 1000 / 20000 ns 13.15 ms, try_wait + nanosleep 64 / 256 / 1000 / 4000 ns 13.21-13.22 ms —
+    // the wait loop is not what bounds the kernel (a waiting warp only uses issue slots nobody else had a use for)
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SGPMP_SPLIT_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -67,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "n"(SGPMP_SPLIT_SLEEP_NS)
         : "memory");
+#endif
 }
 
 __device__ __forceinline__ F2 ld_f2(const float* p) { const float2 v = *reinterpret_cast<const float2*>(p); return f2(v.x, v.y); }
