@@ -307,7 +307,7 @@ cost_st_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, 
             }
             tc.step(P, sm, t, T, x, y, y + N, bvec + t * DP);
             real v = tc.partial(P, sm, T, t);
-            if (t == T - 1 && P.has_ee) {
+            if (CHAIN >= 0 && t == T - 1 && P.has_ee) {
                 real q[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) q[i] = x[i];
@@ -363,8 +363,10 @@ static int launch_cost_st(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc
             return P.has_self ? launch_cost_st_n<real, 7, 2>(sh, P, tables, samples, means, costs, st, pdl)
                               : launch_cost_st_n<real, 7, 1>(sh, P, tables, samples, means, costs, st, pdl);
     }
+    const bool state_only = !P.has_spheres && !P.has_self && !P.has_ee;
     switch (sh.n_dof) {
-#define SGPMP_DOF_CASE(N) case N: return launch_cost_st_n<real, N, 0>(sh, P, tables, samples, means, costs, st, pdl);
+#define SGPMP_DOF_CASE(N) case N: return state_only ? launch_cost_st_n<real, N, -1>(sh, P, tables, samples, means, costs, st, pdl) \
+                                                    : launch_cost_st_n<real, N, 0>(sh, P, tables, samples, means, costs, st, pdl);
 #include "sgpmp_dof_list.inc"
 #undef SGPMP_DOF_CASE
         default:
@@ -455,8 +457,12 @@ static int launch_cost(const sgpmp_shape_t& sh, const sgpmp_cost_desc_t& desc, c
             return P.has_self ? launch_cost_n<real, 7, 2>(sh, P, tables, samples, means, costs, terms, st)
                               : launch_cost_n<real, 7, 1>(sh, P, tables, samples, means, costs, terms, st);
     }
+    // no link fields and no EE goal: the instantiation without any FK / field code (the generic one carries ~4,000 instructions
+    // of it, a stack frame and spills through the hot loop: planar K3 126 -> see profiles/r2 instructions per (sample, step))
+    const bool state_only = !P.has_spheres && !P.has_self && !P.has_ee;
     switch (sh.n_dof) {
-#define SGPMP_DOF_CASE(N) case N: return launch_cost_n<real, N, 0>(sh, P, tables, samples, means, costs, terms, st);
+#define SGPMP_DOF_CASE(N) case N: return state_only ? launch_cost_n<real, N, -1>(sh, P, tables, samples, means, costs, terms, st) \
+                                                    : launch_cost_n<real, N, 0>(sh, P, tables, samples, means, costs, terms, st);
 #include "sgpmp_dof_list.inc"
 #undef SGPMP_DOF_CASE
         default:

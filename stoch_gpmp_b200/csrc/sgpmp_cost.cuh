@@ -185,6 +185,7 @@ __device__ __noinline__ real ee_se3_cost(const CostParams<real>& P, const real* 
 }
 
 // ---- structured chains ------------------------------------------------------------------------------
+// CHAIN = -1: no link fields, no EE goal (planar occupancy map or no obstacle cost): the FK / field code is not compiled in at all.
 // CHAIN = 0: generic serial arm (fk_visit_links, runtime constants).
 // CHAIN = 1 (spheres only) / 2 (+ self-collision code): "Panda structure" (7 joints): fixed rotations are
 // identity / Rx(+-90 deg) / about-z, and most translation components are zero (panda_arm_no_gripper.urdf).
@@ -476,7 +477,9 @@ struct TrajCost {
                     map_pending = map_value(P, sm, x[0], x[1]);
                 }
             }
-            if (P.has_spheres || P.has_self) link_fields(P, sm, x);
+            if constexpr (CHAIN >= 0) {        // CHAIN -1: no link fields and no EE goal are compiled in (state-only costs)
+                if (P.has_spheres || P.has_self) link_fields(P, sm, x);
+            }
         }
         if (t == T - 1 && P.has_goal) {
 #pragma unroll
@@ -512,7 +515,7 @@ struct TrajCost {
         c_self = c_self * P.self_w_coll;
         c_is = (c_is + sm.mub) * P.temperature;
         // EE SE(3) goal on the last state (xp holds x_{T-1} after the final step); scalar value types only
-        if constexpr (VT<V>::W == 1) {
+        if constexpr (VT<V>::W == 1 && CHAIN >= 0) {
             if (P.has_ee) {
                 real q[N];      // a COPY: taking the address of xp itself would demote the whole previous-state array to local memory
 #pragma unroll
