@@ -130,48 +130,73 @@ local_stats_kernel(int S, int M, real tau, const real* __restrict__ costs, const
     }
 }
 
-// mu += step * L (A / Z): one thread per (particle, DoF) runs the banded recurrence over t.
+// mu += step * L (A / Z).  One CTA per particle, three phases: (1) all threads merge and normalise the M entries of A — coalesced
+// over the entry index — and stage the particle's mean and the (G, H) tables in shared memory; (2) one thread per DoF runs the banded
+// recurrence over t out of shared memory; (3) all threads write grad and the updated mean back, coalesced.
 // n_ranks > 1: `stats` holds the gathered blocks [n_ranks][n_particles][M + 2] of the split-particle exchange; they are merged
 // here by log-sum-exp in a fixed rank order (m = max_r m_r, Z = sum_r Z_r e^(m_r - m), A = sum_r A_r e^(m_r - m)) — every rank
 // computes the identical update, no host arithmetic in between.
+// (Round 2's first form gave a (particle, DoF) to ONE thread that walked T steps with 2 R strided loads and a read-modify-write
+// of the mean in every step: 64 problems, R = 8: 176 us per launch — more than half of a split-mode iteration; same expressions,
+// same results here.)
 template <typename real>
-__global__ void apply_stats_kernel(int n_particles, int T, int n, const double* __restrict__ tab, real step,
-                                   const real* __restrict__ stats, int n_ranks, real* __restrict__ means, real* __restrict__ grad) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_particles * n) return;
-    const int bp = idx / n, i = idx - bp * n;
-    const int d = 2 * n;
-    const size_t M = (size_t)T * d;
+__global__ void __launch_bounds__(256)
+apply_stats_kernel(int n_particles, int T, int n, const double* __restrict__ tab, real step,
+                   const real* __restrict__ stats, int n_ranks, real* __restrict__ means, real* __restrict__ grad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = 2 * n, M = T * d;
+    real* a = reinterpret_cast<real*>(smem_raw);     // [M] merged A / Z, then grad
+    real* mu = a + M;                                // [M]
+    real* gh = mu + M;                               // [T][7]
+    real* scale = gh + (size_t)T * 7;                // [n_ranks] e^(m_r - m)
+    __shared__ real s_invZ;
+    const int bp = blockIdx.x;
     const size_t rank_stride = (size_t)n_particles * (M + 2);
     const real* st = stats + (size_t)bp * (M + 2);
-    real m = st[0];
-    for (int r = 1; r < n_ranks; ++r) m = sg_max(m, st[r * rank_stride]);
-    real Z = 0;
-    for (int r = 0; r < n_ranks; ++r) Z += st[r * rank_stride + 1] * sg_exp(st[r * rank_stride] - m);
-    const real invZ = (real)1 / Z;
-    real yp = 0, yv = 0;
-    for (int t = 0; t < T; ++t) {
-        const double* r = tab + (size_t)t * SGPMP_TABLE_STRIDE;
-        real ep = 0, ev = 0;
-        if (n_ranks == 1) {
-            ep = st[2 + t * d + i];
-            ev = st[2 + t * d + n + i];
-        } else {
-            for (int q = 0; q < n_ranks; ++q) {
-                const real sc = sg_exp(st[q * rank_stride] - m);
-                ep += st[q * rank_stride + 2 + t * d + i] * sc;
-                ev += st[q * rank_stride + 2 + t * d + n + i] * sc;
-            }
+    if (threadIdx.x == 0) {
+        real m = st[0];
+        for (int r = 1; r < n_ranks; ++r) m = sg_max(m, st[r * rank_stride]);
+        real Z = 0;
+        for (int r = 0; r < n_ranks; ++r) {
+            const real sc = sg_exp(st[r * rank_stride] - m);
+            scale[r] = sc;
+            Z += st[r * rank_stride + 1] * sc;
         }
-        ep *= invZ; ev *= invZ;
-        const real np_ = (real)r[SGPMP_TAB_G11] * ep - ((real)r[SGPMP_TAB_H11] * yp + (real)r[SGPMP_TAB_H12] * yv);
-        const real nv_ = (real)r[SGPMP_TAB_G21] * ep + (real)r[SGPMP_TAB_G22] * ev -
-                         ((real)r[SGPMP_TAB_H21] * yp + (real)r[SGPMP_TAB_H22] * yv);
-        yp = np_; yv = nv_;
-        const size_t op = (size_t)bp * M + t * d + i, ov = op + n;
-        if (grad) { grad[op] = yp; grad[ov] = yv; }
-        means[op] += step * yp;
-        means[ov] += step * yv;
+        s_invZ = (real)1 / Z;
+    }
+    for (int k = threadIdx.x; k < T * 7; k += blockDim.x) gh[k] = (real)tab[(size_t)(k / 7) * SGPMP_TABLE_STRIDE + (k % 7)];
+    for (int k = threadIdx.x; k < M; k += blockDim.x) mu[k] = means[(size_t)bp * M + k];
+    __syncthreads();
+    const real invZ = s_invZ;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        real e = 0;
+        if (n_ranks == 1) {
+            e = st[2 + k];
+        } else {
+            for (int q = 0; q < n_ranks; ++q) e += st[q * rank_stride + 2 + k] * scale[q];
+        }
+        a[k] = e * invZ;
+    }
+    __syncthreads();
+    if (threadIdx.x < n) {
+        const int i = threadIdx.x;
+        real yp = 0, yv = 0;
+        for (int t = 0; t < T; ++t) {
+            const real* r = gh + t * 7;          // g11 g21 g22 h11 h12 h21 h22
+            const real ep = a[t * d + i], ev = a[t * d + n + i];
+            const real np_ = r[0] * ep - (r[3] * yp + r[4] * yv);
+            const real nv_ = r[1] * ep + r[2] * ev - (r[5] * yp + r[6] * yv);
+            yp = np_; yv = nv_;
+            a[t * d + i] = yp;
+            a[t * d + n + i] = yv;
+            mu[t * d + i] += step * yp;
+            mu[t * d + n + i] += step * yv;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        if (grad) grad[(size_t)bp * M + k] = a[k];
+        means[(size_t)bp * M + k] = mu[k];
     }
 }
 
@@ -204,9 +229,14 @@ template <typename real>
 static int launch_apply_stats(const sgpmp_shape_t& sh, const double* tables, double step, const void* stats, void* means,
                               void* grad, cudaStream_t st, int n_ranks = 1) {
     const int n_particles = sh.B * sh.G * sh.K;
-    const int total = n_particles * sh.n_dof, bs = 64;
-    apply_stats_kernel<real><<<(total + bs - 1) / bs, bs, 0, st>>>(n_particles, sh.T, sh.n_dof, tables, (real)step,
-                                                                  (const real*)stats, n_ranks, (real*)means, (real*)grad);
+    const size_t M = (size_t)sh.T * 2 * sh.n_dof;
+    const size_t smem = (2 * M + (size_t)sh.T * 7 + (size_t)n_ranks) * sizeof(real);
+    if (smem > SGPMP_SMEM_OPTIN) {
+        if (smem > 227 * 1024) { set_error("sgpmp_apply_stats: T=%d too large for shared memory", sh.T); return SGPMP_ERR_UNSUPPORTED; }
+        cudaFuncSetAttribute(apply_stats_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    apply_stats_kernel<real><<<(unsigned)n_particles, 256, smem, st>>>(n_particles, sh.T, sh.n_dof, tables, (real)step,
+                                                                      (const real*)stats, n_ranks, (real*)means, (real*)grad);
     SGPMP_CHECK_LAUNCH("sgpmp_apply_stats");
     return SGPMP_OK;
 }
