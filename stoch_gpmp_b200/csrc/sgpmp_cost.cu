@@ -203,25 +203,16 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
     tc.begin();
     const real* xs = samples + (size_t)bp * T * d * S + s;
     real* my = ring + threadIdx.x;
-    int wr = 0, rd = 0;                                   // ring slots of the next step to load / to consume
-    auto issue = [&](int t) {
-        real* dst = my + (size_t)wr * d * 128;
-        wr = (wr + 1 == DEPTH) ? 0 : wr + 1;
+    auto issue = [&](int t, int slot_w) {                 // step t into ring slot slot_w
+        real* dst = my + (size_t)slot_w * d * 128;
         const real* src = xs + (size_t)t * d * S;
 #pragma unroll
         for (int j = 0; j < d; ++j) cp_async<sizeof(real)>(dst + j * 128, src + (size_t)j * S);
     };
-#pragma unroll
-    for (int k = 0; k < DEPTH - 1; ++k) {
-        if (k < T) issue(k);
-        cp_async_commit();
-    }
-    for (int t = 0; t < T; ++t) {
-        if (t + DEPTH - 1 < T) issue(t + DEPTH - 1);      // into the slot step t - 1 was read from
+    auto consume = [&](int t, int slot_r) {               // step t out of ring slot slot_r = t % DEPTH
         cp_async_commit();                                // (an empty group near the end keeps the group count uniform)
         cp_async_wait<DEPTH - 1>();                       // the group of step t has landed
-        const real* slot = my + (size_t)rd * d * 128;
-        rd = (rd + 1 == DEPTH) ? 0 : rd + 1;
+        const real* slot = my + (size_t)slot_r * d * 128;
         real x[d], y[d];
 #pragma unroll
         for (int j = 0; j < d; ++j) {
@@ -229,6 +220,31 @@ cost_kernel(const __grid_constant__ CostParams<real> P, int G, int K, int S, int
             y[j] = means ? x[j] - mu[t * d + j] : x[j];
         }
         tc.step(P, sm, t, T, x, y, y + N, means ? bvec + t * DP : nullptr);
+    };
+#pragma unroll
+    for (int k = 0; k < DEPTH - 1; ++k) {
+        if (k < T) issue(k, k);
+        cp_async_commit();
+    }
+    if constexpr (CHAIN < 0) {
+        // state-only body (short): the time loop is unrolled by the ring depth, so slot addresses are immediates
+        for (int t0 = 0; t0 < T; t0 += DEPTH) {
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {
+                const int t = t0 + k;
+                if (t < T) {
+                    if (t + DEPTH - 1 < T) issue(t + DEPTH - 1, (k + DEPTH - 1) % DEPTH);      // the slot step t - 1 was read from
+                    consume(t, k);
+                }
+            }
+        }
+    } else {
+        int wr = DEPTH - 1, rd = 0;                       // ring slots of the next step to load / to consume
+        for (int t = 0; t < T; ++t) {
+            if (t + DEPTH - 1 < T) { issue(t + DEPTH - 1, wr); wr = (wr + 1 == DEPTH) ? 0 : wr + 1; }
+            consume(t, rd);
+            rd = (rd + 1 == DEPTH) ? 0 : rd + 1;
+        }
     }
     tc.finish(P, sm, T);
     const size_t o = (size_t)bp * S + s;
