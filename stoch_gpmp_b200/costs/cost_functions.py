@@ -366,6 +366,8 @@ class CostComposite(Cost):
         out = {nm: terms[i].reshape(-1) for i, nm in enumerate(_lib.TERM_NAMES)}
         out['gp+start'] = out['start'] + out['gp']
         out['total'] = costs.reshape(-1)
+        if low.custom:       # user-defined terms of cost_list (torch code, the reference's calling convention)
+            out['total'] = out['total'] + torch.as_tensor(low.custom_costs(x, **observation), device=x.device).to(x.dtype).reshape(-1)
         return out
 
     def eval(self, trajs, **observation):

@@ -976,3 +976,38 @@ def test_lowlat_iteration_equals_separate_kernels(name, cuda):
     mu_2 = torch.tensor(g[pre + 'it0_means_pre'][None], device=cuda)
     _ops().iterate(sh, desc, tab, spec['step_size'], 2, mu_2, seed=11, draw0=0, lowlat=True)
     assert torch.equal(mu_2, mu)
+
+
+def test_lowlat_dependent_launch_chain_equals_serial_launches(cuda, tmp_path):
+    """The low-latency iteration chains its three kernels by programmatic dependent launch (each may start while its predecessor
+    drains and waits — griddepcontrol.wait — before its first dependent access).  $SGPMP_PDL is read once per process, so the two
+    forms run in two subprocesses: 60 iterations of one Panda problem and of the shipped fp64 planar problem must give bit-identical
+    means and costs (a missing wait would show up as a race between iterations)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import bench
+dev = torch.device("cuda:0")
+out = {}
+for name in ("panda", "planar_shipped"):
+    w = bench.workload(name, 1)
+    pl = bench.build_planner(w, 1, dev)
+    obs = {"obstacle_spheres": torch.tensor(w["spheres"], dtype=torch.float32, device=dev)} if w["spheres"] is not None else {}
+    for rep in range(3):
+        r = pl.optimize(opt_iters=20, return_samples=False, **obs)
+    out[name + "_means"] = pl._means.cpu()
+    out[name + "_costs"] = r[4].cpu()
+torch.save(out, sys.argv[1])
+''' % root
+    res = []
+    for flag in ("0", "1"):
+        f = str(tmp_path / ("pdl%s.pt" % flag))
+        env = dict(os.environ, SGPMP_PDL=flag, SGPMP_LOWLAT="1")
+        subprocess.run([sys.executable, "-c", script, f], check=True, env=env, timeout=300)
+        res.append(torch.load(f))
+    for k in res[0]:
+        assert torch.equal(res[0][k], res[1][k]), k

@@ -304,6 +304,9 @@ def test_user_defined_cost_terms(name, cuda):
         assert float(extra.abs().max()) > 0
         # the totals differ by exactly the user term (to the rounding of the fp32 totals themselves)
         assert float(((o_fk[4] - o_rf[4]) - extra).abs().max()) < (1e-5 if f32 else 1e-12) * float(o_fk[4].abs().max())
+        # CostComposite.eval() (drop-in use) carries the user term too
+        ev = comp_fk.eval(x, **obs) - comp.eval(x, **obs)
+        assert float((ev - extra.reshape(-1)).abs().max()) < (1e-5 if f32 else 1e-12) * float(comp.eval(x, **obs).abs().max())
         # GPMP and the split-particle mode need kernels for every term
         with pytest.raises(NotImplementedError):
             pl_fk.optimize_split(**obs)
