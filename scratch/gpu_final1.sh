@@ -3,10 +3,8 @@
 export PYTHONPATH=$PWD
 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2z_gputest.txt
 python bench.py > gpurun_out/r2z_bench_n1.json 2> gpurun_out/r2z_bench_n1.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2z_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r2z_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2z_launch_bench.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:iterate_split -c 1 -o gpurun_out/r2z_split -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r2z_ncu_split.log 2>&1
 python bench_kernels.py --workload panda > gpurun_out/r2z_kernels_panda.jsonl 2>/dev/null
 python bench_kernels.py --workload planar > gpurun_out/r2z_kernels_planar.jsonl 2>/dev/null
 python bench_c5.py > gpurun_out/r2z_c5.jsonl 2>/dev/null

@@ -2,8 +2,11 @@
 
 Here they are PARAMETER CARRIERS: `StochGPMP` lowers `CostComposite.cost_list` into the POD descriptor
 `sgpmp_cost_desc_t` consumed by the fused CUDA kernel (csrc/sgpmp_cost.cuh).  `eval()` is kept for
-drop-in use and runs the standalone CUDA cost kernel (K3); anything that cannot be lowered raises
-NotImplementedError — there is no CPU fallback.
+drop-in use and runs the standalone CUDA cost kernel (K3); fields / FK callables that a lowered term needs
+but the kernels cannot evaluate raise NotImplementedError — there is no CPU fallback.  A `cost_list` entry
+that is not one of these classes but is callable is a USER term (the reference accepts any callable,
+cost_functions.py:47-56): it runs as the user's own torch code on the materialised samples, next to the
+kernels' terms (LoweredCost.custom_costs, planner.StochGPMPBatch._optimize_separate).
 
   CostGP          <- cost_functions.py:88-146     CostGoalPrior <- cost_functions.py:340-388
   CostCollision   <- cost_functions.py:221-261    CostComposite <- cost_functions.py:32-58

@@ -8,6 +8,7 @@ Host code only carries parameters and launches kernels through the C-ABI (ops.py
   reset()      -> K1 sgpmp_prior_factor (init + sampling prior), K2 sgpmp_sample (initial means)
   optimize()   -> sgpmp_iterate (fused sample + cost + softmax + update, opt_iters per launch)
   sample_and_eval / _update_distribution / sample_trajectories -> K2 / K3 / K4
+  optimize() with user-defined terms in cost_list             -> K2, K3 (+ the user's torch code), K4 per iteration
 There is no CPU path: a CPU `tensor_args['device']` raises.
 
 Differences from the reference that a user can observe:
