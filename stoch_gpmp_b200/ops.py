@@ -143,16 +143,19 @@ def update(shape, temperature, step_size, costs, samples, means):
 
 
 def iterate(shape, desc, tables, step_size, n_iters, means, eps_in=None, seed=0, draw0=0,
-            want_samples=False, want_costs=True, want_weights=True, want_grad=True, want_means_pre=True, lowlat=False):
+            want_samples=False, want_costs=True, want_weights=True, want_grad=True, want_means_pre=True, lowlat=False,
+            validate=True):
     """Fused loop.  Updates `means` in place.  Returns dict(means_pre, samples, costs, weights, grad) of the
-    LAST iteration (entries not requested are None)."""
+    LAST iteration (entries not requested are None).  validate=False skips the argument checks (the planner passes its
+    own tensors; the checks are ~2 us of a host-bound call)."""
     lib = _lib.load()
     B, NP, T, d, S = shape.B, shape.G * shape.K, shape.T, 2 * shape.n_dof, shape.S
     dt, dev = means.dtype, means.device
-    _req(tables, "tables", torch.float64, (T, _lib.TABLE_STRIDE))
-    _req(means, "means", None, (B, NP, T, d))
-    if eps_in is not None:
-        _req(eps_in, "eps_in", dt, (n_iters, B, NP, T, d, S))
+    if validate:
+        _req(tables, "tables", torch.float64, (T, _lib.TABLE_STRIDE))
+        _req(means, "means", None, (B, NP, T, d))
+        if eps_in is not None:
+            _req(eps_in, "eps_in", dt, (n_iters, B, NP, T, d, S))
     if lowlat:
         # few problems: three short launches per iteration instead of the thread-per-sample fused kernel (csrc/sgpmp_lowlat.cu)
         out = dict(means_pre=torch.empty_like(means) if want_means_pre else None,

@@ -119,7 +119,7 @@ class StochGPMPBatch:
         if not _lib.load().sgpmp_dof_supported(n_dof):
             raise NotImplementedError("n_dof=%d is not instantiated in the CUDA library (csrc/sgpmp_dof_list.inc)" % n_dof)
 
-        self._weights = None
+        self._weights_raw = None
         self._last = None
         self.reset(start_state, multi_goal_states, initial_particle_means=initial_particle_means)
 
@@ -224,6 +224,8 @@ class StochGPMPBatch:
         self._Sigma_inv = None
         self._last = None
         self._shape_cache = None
+        import os
+        self._lowlat_env = os.environ.get("SGPMP_LOWLAT")      # read once per reset(): optimize() is host-bound for one problem
         self._warm_kernels()
 
     _warm = True        # GPMPBatch (another algorithm on the same state) switches the warm-up off
@@ -259,6 +261,16 @@ class StochGPMPBatch:
         return t
 
     @property
+    def _weights(self):
+        """Softmax weights of the last iteration as the reference keeps them, [NP, S, 1, 1] (planner.py:264-266).  Built on
+        access: every tensor view costs the host ~1.2 us, and optimize() is host-bound when it is called once per iteration."""
+        w = self._weights_raw
+        if w is None:
+            return None
+        w = self._out(w)
+        return w.reshape(*w.shape, 1, 1)
+
+    @property
     def particle_means(self):
         return self._out(self._means)
 
@@ -274,7 +286,10 @@ class StochGPMPBatch:
     @property
     def state_samples(self):
         if self._state_samples is None:
-            self._state_samples = self._materialise(self._state_samples_src)
+            if self._state_samples_src is None:       # the last optimize() wrote its samples: view of the S-minor buffer
+                self._state_samples = self._samples_sminor.permute(0, 1, 4, 2, 3)
+            else:
+                self._state_samples = self._materialise(self._state_samples_src)
         return self._out(self._state_samples)
 
     @property
@@ -352,15 +367,13 @@ class StochGPMPBatch:
         costs = costs.reshape(self.num_problems, self.num_particles, self.num_samples).contiguous()
         grad, w = ops.update(self._shape(), self.temperature, self.step_size, costs, self._samples_sminor, self._means)
         self._weights_raw = w
-        self._weights = self._out(w).reshape(*self._out(w).shape, 1, 1)
         return self._out(grad)
 
     def _lowlat(self, n_iters):
         """Few problems (the reference's own use: ONE): the fused kernel's thread-per-sample mapping would leave the GPU idle, so
         optimize() runs the low-latency form (three short launches per iteration, csrc/sgpmp_lowlat.cu).  $SGPMP_LOWLAT=0/1
         overrides the choice."""
-        import os
-        env = os.environ.get("SGPMP_LOWLAT")
+        env = self._lowlat_env
         if env is not None:
             return env != "0"
         # measured on B200, us per iteration, fused (cluster) form -> low-latency form: one Panda problem 89.9 -> 31.2, one planar
@@ -401,7 +414,8 @@ class StochGPMPBatch:
                     out['samples'] = None
             else:
                 out = ops.iterate(sh, desc, self._tables, self.step_size, c, self._means, eps_in=eps, seed=self.seed,
-                                  draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat(c))
+                                  draw0=self._draw, want_samples=bool(return_samples and last_chunk), lowlat=self._lowlat(c),
+                                  validate=eps is not None)
                 self._draw += c
             done += c
             if debug:
@@ -409,20 +423,24 @@ class StochGPMPBatch:
         self._last = dict(means_pre=out['means_pre'], draw=self._draw - 1, eps=None if _eps is None else _eps[-1],
                           samples=out['samples'])
         self._weights_raw = out['weights']
-        self._weights = self._out(out['weights']).reshape(*self._out(out['weights']).shape, 1, 1)
         pos_s = vel_s = None
         if out['samples'] is not None:
-            ss = out['samples'].permute(0, 1, 4, 2, 3)
-            self._state_samples = ss
-            self._samples_sminor = out['samples']
-            pos_s, vel_s = self._out(ss[..., :n]), self._out(ss[..., -n:])
+            # views are built from the per-problem tensor when there is no batch axis to return: every view costs the host ~1.2 us
+            # and this call is host-bound in the reference's usage (one optimize() per iteration); `state_samples` builds its
+            # [B,NP,S,T,d] view on access
+            xs = out['samples']
+            ss = xs.permute(0, 1, 4, 2, 3) if self._batched else xs[0].permute(0, 3, 1, 2)
+            self._samples_sminor = xs
+            self._state_samples = None
+            self._state_samples_src = None
+            pos_s, vel_s = ss[..., :n], ss[..., -n:]
         elif _eps is None:
             # nothing was written: `state_samples` (and _get_traj) regenerate THIS iteration's samples lazily from the RNG
             # counters, so that they always pair with the weights of the same iteration
             self._state_samples = None
             self._state_samples_src = (out['means_pre'], self._draw - 1, self.num_samples)
-        mp = out['means_pre']
-        return (self._out(mp[..., :n]), self._out(mp[..., -n:]), pos_s, vel_s, self._out(out['costs']), self._out(out['grad']))
+        mp = self._out(out['means_pre'])
+        return (mp[..., :n], mp[..., -n:], pos_s, vel_s, self._out(out['costs']), self._out(out['grad']))
 
     def optimize_split(self, opt_iters=None, group=None, return_samples=False, **observation):
         """Split-particle mode (SURVEY §8e): the S samples of every particle are divided over the ranks of `group`;
