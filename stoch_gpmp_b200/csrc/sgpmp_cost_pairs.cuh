@@ -150,6 +150,9 @@ struct TrajCostPairs {
     // load (not even the byte -> float conversion), so its L1/L2 latency hides behind the next step's RNG and recurrence
     // (ncu: the gather's consumer carried 23 % of the planar kernel's stall samples).  Occupancy sums are small integers,
     // exact in any order: bit-identical to the in-order sum.
+    // MODE 0: byte or float map decided at run time; 1: byte map; 2: float map (the state-only fused kernel picks the mode once
+    // per sweep, so the per-step pointer test and the predicated twin of the gather disappear from its hot loop)
+    template <int MODE = 0>
     __device__ __forceinline__ void map_gather_deferred(const CostParams<float>& P, const CostSmem<float>& sm, float x, float y) {
         const float xo = sg_mul_add_2r(x, P.map_inv_cell, P.map_origin_x);
         const float yo = sg_mul_add_2r(y, P.map_inv_cell, P.map_origin_y);
@@ -157,7 +160,7 @@ struct TrajCostPairs {
         ix = min(max(ix, 0), P.map_h - 1);
         iy = min(max(iy, 0), P.map_w - 1);
         const int idx = iy * P.map_w + ix;
-        if (sm.map_u8) {
+        if (MODE == 1 || (MODE == 0 && sm.map_u8)) {
             c_coll += (float)map_pending_u8;
             map_pending_u8 = __ldg(sm.map_u8 + idx);
         } else {

@@ -238,6 +238,10 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
         const bool emit = last && A.samples != nullptr;
         for (int sw = 0; sw < n_sweeps; ++sw) {
             if (role == 0) {
+              // MM: occupancy-map mode of this sweep — -1 none, 1 byte map, 2 float map (state-only form; a compile-time constant of
+              // the time loop instead of a per-step test)
+              auto state_sweep = [&](auto mm_) {
+                constexpr int MM = decltype(mm_)::value;
                 const int sl = sw * SW + wa * 32 + lane;
                 const bool valid = sl < ns;
                 const int s0 = valid ? sl : ns - 1;              // idle lanes shadow the last sample, results dropped
@@ -335,9 +339,9 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                             cis = vfma(yp[k], bp_, vfma(yv[k], bv_, cis));
                             if (NB > 0 && k < 3) st_f2(slot + 32 * k, ld_f2(blk + 8 + 12 * k + REC_M) + yp[k]);   // q_t[2k], q_t[2k+1] for the link warp
                         }
-                        if (NB == 0 && P.has_map) {
+                        if constexpr (NB == 0 && MM > 0) {
                             const F2 x01 = ld_f2(blk + 8 + REC_M) + yp[0];
-                            tcm.map_gather_deferred(P, sm, lane0(x01), lane1(x01));
+                            tcm.template map_gather_deferred<MM>(P, sm, lane0(x01), lane1(x01));
                         }
                         if (emit && valid) emit_row(t);
                     }
@@ -391,6 +395,14 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                     wsm[sl] = c;
                     if (last && A.costs) A.costs[(size_t)bp * S + sl] = c;
                 }
+              };
+              if constexpr (NB == 0) {
+                  if (!P.has_map) state_sweep(std::integral_constant<int, -1>{});
+                  else if (sm.map_u8) state_sweep(std::integral_constant<int, 1>{});
+                  else state_sweep(std::integral_constant<int, 2>{});
+              } else {
+                  state_sweep(std::integral_constant<int, -1>{});
+              }
             } else if constexpr (NB > 0) {
                 // ================= link warps =================
                 // per stage: the R state warps this warp serves, in turn; the stage's link-field sums are folded into the
