@@ -191,6 +191,49 @@ def test_batch_equals_loop_of_singles(cuda):
         assert torch.equal(os_[4], ob[4][b]) and torch.equal(os_[5], ob[5][b])
 
 
+def test_user_defined_term_on_a_problem_batch(cuda):
+    """A user term on StochGPMPBatch sees trajs [B*NP*S, T, d] in (problem, particle, sample) order: a batch of B problems with a
+    user-written velocity penalty == B single planners with the same term (problem_offset = b), over two iterations."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, CostGoalPrior
+    from stoch_gpmp_b200.planner import StochGPMP, StochGPMPBatch
+    from stoch_gpmp_b200.scenarios import PLANAR_COST, PLANAR_SIGMAS, planar_batch
+    B, G, K, S, T, n = 3, 2, 2, 16, 16, 2
+    ta = dict(device=cuda, dtype=torch.float64)
+    start, goals = planar_batch(B, G, seed0=5)
+    seen = []
+
+    def vel_penalty(trajs, x_trajs=None, **obs):
+        seen.append(tuple(trajs.shape))
+        return 0.25 * (trajs[:, :, n:] ** 2).sum((-1, -2))
+
+    def build(cls, sl, **kw):
+        s = torch.tensor(start[sl], **ta)
+        gl = torch.tensor(goals[sl], **ta)
+        comp = CostComposite(n, T, [
+            CostGP(n, T, s, 0.02, dict(sigma_start=PLANAR_COST['sigma_start'], sigma_gp=PLANAR_COST['sigma_gp']), ta),
+            CostGoalPrior(n, T, multi_goal_states=gl, num_particles_per_goal=K, num_samples=S,
+                          sigma_goal_prior=PLANAR_COST['sigma_goal_prior'], tensor_args=ta),
+            vel_penalty])
+        return cls(num_particles_per_goal=K, num_samples=S, traj_len=T, opt_iters=2, dt=0.02, n_dof=n, step_size=0.5,
+                   temperature=1., start_state=s, multi_goal_states=gl, cost=comp, seed=3, tensor_args=ta, **PLANAR_SIGMAS, **kw)
+    pb = build(StochGPMPBatch, slice(0, B))
+    ob = pb.optimize()
+    assert seen and seen[-1] == (B * G * K * S, T, 2 * n)
+    for b in range(B):
+        ps = build(StochGPMP, b, problem_offset=b)
+        os_ = ps.optimize()
+        assert seen[-1] == (G * K * S, T, 2 * n)
+        assert rel(ps.particle_means.cpu().numpy(), pb.particle_means[b].cpu().numpy()) < 1e-13
+        assert rel(os_[4].cpu().numpy(), ob[4][b].cpu().numpy()) < 1e-13
+    # the penalty is really in the costs: the same batch without it differs
+    pb0 = build(StochGPMPBatch, slice(0, B))
+    pb0.cost.cost_list.pop()
+    pb0 = StochGPMPBatch(num_particles_per_goal=K, num_samples=S, traj_len=T, opt_iters=2, dt=0.02, n_dof=n, step_size=0.5, temperature=1.,
+                         start_state=torch.tensor(start, **ta), multi_goal_states=torch.tensor(goals, **ta), cost=pb0.cost, seed=3,
+                         tensor_args=ta, **PLANAR_SIGMAS)
+    assert not torch.equal(pb0.optimize()[4], ob[4])
+
+
 def test_error_behaviour(cuda, lib):
     from stoch_gpmp_b200.costs.cost_functions import CostComposite, CostGP, Cost
     from stoch_gpmp_b200.planner import StochGPMP
