@@ -308,7 +308,10 @@ def extra_configs(dev, peaks, flush):
     r = roofline_block(w, nt, ms, peaks, 1024)
     out["planar_1024"] = {"workload": "C2: planar 2-DoF batched, 1024 problems x 4 goals x 256 samples x T 64, fp32", "ms_per_step": ms,
                           "value": nt / (ms * 1e-3), "unit": UNIT,
-                          "roofline": {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "frac_of_nominal", "algorithmic_flops_per_traj_sample", "mufu", "binding")}}
+                          "roofline": dict({k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "frac_of_nominal", "algorithmic_flops_per_traj_sample", "mufu", "binding", "traffic", "traffic_source", "ncu")},
+                                           note="issue-bound, not pipe-bound: ~110 instructions per (sample, step), 59 of them the Philox / Box-Muller draw of "
+                                                "the four normals (integer work that the algorithmic FLOP / MUFU counts do not contain); the utilisation to "
+                                                "read is ncu.issue_active_pct")}
     del pl
     # C3: one Panda problem, 4 goals x 512 samples (per-iteration latency + the 400-iteration plan)
     w = workload("panda", 1)
