@@ -85,6 +85,26 @@ class CostCollision(Cost):
         self.sigma_coll = sigma_coll
         self.tensor_args = tensor_args
 
+    def eval_torch(self, trajs, x_trajs=None, **observation):
+        """This term in torch over time steps 1..T-1 (see _field_term_torch): the path of an un-lowerable FK / field."""
+        return _field_term_torch(self, self.field, self.sigma_coll, 1, self.traj_len, trajs, x_trajs,
+                                 obstacle_spheres=observation.get('obstacle_spheres', None))
+
+
+def _field_term_torch(cost, field, sigma, lo, hi, trajs, x_trajs, **observations):
+    """(1 / sigma^2) * sum_t field.compute_cost(states_t) over the time range [lo, hi) — the arithmetic of the reference's
+    FieldFactor.get_error + CostCollision / CostGoal.eval (factors/field_factor.py:20-34, cost_functions.py:247-261, :308-321) in torch,
+    for a term the kernels cannot lower (an FK callable that is not a SerialChainFK, or a user-written field object)."""
+    batch = trajs.shape[0]
+    if x_trajs is not None:
+        states = x_trajs[:, lo:hi]
+    else:
+        states = trajs[:, lo:hi, :cost.n_dof].reshape(-1, cost.n_dof)
+    err = field.compute_cost(states, **observations)
+    if not isinstance(err, torch.Tensor):       # e.g. LinkDistanceField without spheres returns 0 (fields.py:64-65)
+        return torch.zeros(batch, dtype=trajs.dtype, device=trajs.device)
+    return err.reshape(batch, hi - lo).sum(1) / float(sigma) ** 2
+
 
 class CostGoal(Cost):
     """End-effector goal factor on the LAST time step (FieldFactor range [T-1, T], cost_functions.py:300-304):
@@ -97,6 +117,10 @@ class CostGoal(Cost):
         self.field = field
         self.sigma_goal = sigma_goal
         self.tensor_args = tensor_args
+
+    def eval_torch(self, trajs, x_trajs=None, **observation):
+        """This term in torch on the last time step (see _field_term_torch): the path of an un-lowerable FK / field."""
+        return _field_term_torch(self, self.field, self.sigma_goal, self.traj_len - 1, self.traj_len, trajs, x_trajs)
 
 
 class CostGPTrajectory(Cost):
@@ -121,6 +145,10 @@ class LoweredCost:
         gp = goal = coll = selfc = ee = None
         self.custom = []
         self.composite_fk = composite.FK
+        # an FK callable that is not a SerialChainFK descriptor (the reference takes ANY callable, cost_functions.py:39-52): the
+        # kernels cannot evaluate it, so every term that needs link frames runs in torch on the materialised samples
+        # (Cost*.eval_torch, fields.*.compute_cost), next to the terms the kernels do evaluate
+        fk_torch_only = callable(composite.FK) and not isinstance(composite.FK, SerialChainFK)
         for c in composite.cost_list:
             if isinstance(c, (CostGP, CostGPTrajectory)):
                 if gp is not None:
@@ -133,6 +161,9 @@ class LoweredCost:
             elif isinstance(c, CostGoal):
                 if c.field is None:
                     continue
+                if callable(composite.FK) and hasattr(c.field, 'compute_cost') and (fk_torch_only or not isinstance(c.field, EESE3DistanceField)):
+                    self.custom.append(c.eval_torch)
+                    continue
                 if not isinstance(c.field, EESE3DistanceField):
                     raise NotImplementedError("CostGoal field %s cannot be lowered to the CUDA path" % type(c.field).__name__)
                 if ee is not None:
@@ -141,6 +172,11 @@ class LoweredCost:
             elif isinstance(c, CostCollision):
                 if c.field is None:
                     continue                      # the reference returns 0 for a field-less collision cost
+                known = isinstance(c.field, (LinkDistanceField, LinkSelfDistanceField, ObstacleMap, list, tuple))
+                if hasattr(c.field, 'compute_cost') and ((fk_torch_only and isinstance(c.field, (LinkDistanceField, LinkSelfDistanceField)))
+                                                         or not known):
+                    self.custom.append(c.eval_torch)      # link field under an arbitrary FK callable, or a user-written field object
+                    continue
                 if isinstance(c.field, LinkSelfDistanceField):
                     if selfc is not None:
                         raise NotImplementedError("more than one self-collision field in cost_list")

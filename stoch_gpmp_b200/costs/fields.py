@@ -22,11 +22,28 @@ def _check_interp(name, num_interpolate, rng):
 
 
 class DistanceField:
+    """The arithmetic of a field normally runs inside the CUDA kernels.  `compute_cost` is the torch form with the
+    reference's signature (link frames [..., L, 4, 4] -> one value per configuration): the planner uses it only for a
+    term the kernels CANNOT lower — a `CostComposite(FK=<any callable>)` that is not a `SerialChainFK`, as the reference
+    allows (cost_functions.py:39-52) — evaluated on the materialised samples like a user-defined term."""
+
     def __init__(self, tensor_args=None):
         self.tensor_args = tensor_args
 
     def zero_grad(self):
         pass
+
+
+def _link_points(link_tensor, num_interpolate, rng):
+    """Link-frame origins [..., L, 3] plus the interpolated points of costs/fields.py:68-74 appended link by link."""
+    pts = link_tensor[..., :3, 3]
+    n = int(num_interpolate)
+    if n > 0:
+        alpha = torch.linspace(0, 1, n + 2)[1:n + 1].to(torch.float32).to(pts.dtype).to(pts.device).reshape(n, 1)
+        for i in range(int(rng[0]), int(rng[1])):
+            a, b = pts[..., i:i + 1, :], pts[..., i + 1:i + 2, :]
+            pts = torch.cat([pts, a + (b - a) * alpha], dim=-2)
+    return pts
 
 
 class LinkDistanceField(DistanceField):
@@ -58,6 +75,24 @@ class LinkDistanceField(DistanceField):
     def interp_alpha(self):
         return _interp_alpha(self.num_interpolate)
 
+    def compute_cost(self, link_tensor, obstacle_spheres=None, **kwargs):
+        """costs/fields.py:63-86 in torch (see DistanceField): obstacle_spheres [O, 4] or [1, O, 4] = (centre, radius)."""
+        if obstacle_spheres is None:
+            return 0
+        sp = torch.as_tensor(obstacle_spheres).to(link_tensor).reshape(-1, 4)
+        pts = _link_points(link_tensor, self.num_interpolate, self.link_interpolate_range).unsqueeze(-2)     # [..., P, 1, 3]
+        d2 = ((pts - sp[:, :3]) ** 2).sum(-1)                                                                # [..., P, O]
+        if self.field_type == 'rbf':
+            return torch.exp(-0.5 * d2 / sp[:, 3] ** 2).sum((-1, -2))
+        if self.field_type == 'sdf':
+            sdf = sp[:, 3] - d2.sqrt()
+            if self.clamp_sdf:
+                sdf = sdf.clamp(max=0.)
+            return sdf.amax((-1, -2))
+        if self.field_type == 'occupancy':
+            return (d2.sqrt() < sp[:, 3]).sum((-1, -2)).to(link_tensor.dtype)
+        raise NotImplementedError("LinkDistanceField(field_type=%r) is unknown" % (self.field_type,))
+
 
 class LinkSelfDistanceField(DistanceField):
     """sum over ALL ordered pairs of link frames (i == j included) of exp(-|p_i - p_j|^2 / (2 margin^2))
@@ -74,6 +109,12 @@ class LinkSelfDistanceField(DistanceField):
 
     def interp_alpha(self):
         return _interp_alpha(self.num_interpolate)
+
+    def compute_cost(self, link_tensor, **kwargs):
+        """costs/fields.py:114-124 in torch (see DistanceField): all ordered pairs of link points, i == j included."""
+        pts = _link_points(link_tensor, self.num_interpolate, self.link_interpolate_range)
+        d2 = ((pts.unsqueeze(-2) - pts.unsqueeze(-3)) ** 2).sum(-1)
+        return torch.exp(-d2 / (2.0 * self.margin ** 2)).sum((-1, -2))
 
 
 class EESE3DistanceField(DistanceField):
@@ -98,6 +139,15 @@ class EESE3DistanceField(DistanceField):
         if H.shape[0] != 1:
             raise NotImplementedError("EESE3DistanceField: one target pose per cost (got %d)" % H.shape[0])
         return H[0]
+
+    def compute_cost(self, link_tensor, **kwargs):
+        """costs/fields.py:142-150 in torch (see DistanceField), with the SE(3) metric the CUDA path uses (class docstring)."""
+        H = link_tensor[..., -1, :, :]
+        Ht = torch.as_tensor(self.target_H).to(H).reshape(-1, 4, 4)[0]
+        dp = torch.linalg.norm(H[..., :3, 3] - Ht[:3, 3], dim=-1)
+        tr = (H[..., :3, :3] * Ht[:3, :3]).sum((-1, -2))
+        dist = self.w_pos * dp + self.w_rot * torch.acos(torch.clamp((tr - 1.0) * 0.5, -1.0, 1.0))
+        return dist * dist if self.square else dist
 
     def check_lowerable(self):
         self.target_matrix()

@@ -148,10 +148,13 @@ def test_cost_lowering_rejects_what_it_cannot_lower():
         CostComposite(7, 8, [gp, CostGoal(7, 8, field=EESE3DistanceField(torch.eye(4)), sigma_goal=1.)], FK=None).lower(
             1, 1, torch.device('cpu'), torch.float32)
     CostComposite(7, 8, [gp, CostGoal(7, 8)]).lower(1, 1, torch.device('cpu'), torch.float32)    # field=None: term dropped
-    # LinkDistanceField without a lowerable FK descriptor
-    comp = CostComposite(7, 8, [gp, CostCollision(7, 8, field=LinkDistanceField(), sigma_coll=1.)], FK=lambda q: q)
-    with pytest.raises(NotImplementedError, match="SerialChainFK"):
-        comp.lower(1, 1, torch.device('cpu'), torch.float32)
+    # LinkDistanceField under an FK callable that is not a SerialChainFK descriptor: not lowered, kept as a torch-evaluated term
+    # (the reference accepts any FK callable, cost_functions.py:39-52; tests/test_gpu_planner.py::test_arbitrary_fk_callable)
+    fk_any = lambda q: q
+    coll_any = CostCollision(7, 8, field=LinkDistanceField(), sigma_coll=1.)
+    low_any = CostComposite(7, 8, [gp, coll_any], FK=fk_any).lower(1, 1, torch.device('cpu'), torch.float32)
+    assert low_any.fk is None and low_any.sphere_sigma is None and len(low_any.custom) == 1
+    assert low_any.custom[0].__self__ is coll_any
     with pytest.raises(NotImplementedError):
         LinkDistanceField(field_type='hinge').check_lowerable()
     with pytest.raises(NotImplementedError):

@@ -191,6 +191,50 @@ def test_batch_equals_loop_of_singles(cuda):
         assert torch.equal(os_[4], ob[4][b]) and torch.equal(os_[5], ob[5][b])
 
 
+@pytest.mark.parametrize("name", ['panda_soft_f64', 'panda_shipped_f64', 'panda_ee_soft_f64', 'panda_interp_f64', 'panda_sdf_f64',
+                                  'panda_soft_f32'])
+def test_arbitrary_fk_callable(name, cuda):
+    """CostComposite(FK=<any callable>) as the reference allows (cost_functions.py:39-52): with an FK that is not a SerialChainFK
+    descriptor the link-field terms (sphere / self-collision / EE goal, with interpolation and the sdf variant) are evaluated in torch
+    on the materialised samples, the GP / goal terms and the IS term still in the CUDA cost kernel.  Same golden costs, gradient and
+    means as the run of the unmodified reference (fp64 1e-10), i.e. as the fully lowered cost list."""
+    from stoch_gpmp_b200.costs.cost_functions import CostComposite
+    from stoch_gpmp_b200.robots import PandaFK
+    g = load(name)
+    spec = OP.spec_from_golden(g)
+    f32 = spec['dtype'] == 'float32'
+    dtype = torch.float32 if f32 else torch.float64
+    pre0 = 'sameL_' if f32 else ''
+    T, n = spec['T'], spec['n_dof']
+    d = 2 * n
+    comp, _ = _lowered(spec, cuda, dtype)
+    chain = PandaFK()
+    calls = []
+
+    def fk(q):                       # a plain function: the planner cannot lower it
+        calls.append(tuple(q.shape))
+        return chain(q)
+    comp_any = CostComposite(n, T, list(comp.cost_list), FK=fk, tensor_args=dict(device=cuda, dtype=dtype))
+    pl = _planner(g, spec, cuda, dtype, cost=comp_any)
+    assert pl._lowered.fk is None and pl._lowered.custom
+    obs = _obs(spec, cuda, dtype)
+    pre = f'{pre0}it0_'
+    pl.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+    eps = torch.tensor(to_sminor(eps_ref_to_traj(g[pre + 'eps'], T, d)), device=cuda)
+    out = pl.optimize(_eps=eps, **obs)
+    assert calls and calls[-1] == (pl.num_particles * spec['S'] * T, n)
+    ftol = FACTOR_TOL_F64.get(name, TOL_F64)
+    if f32:
+        ref = _planner(g, spec, cuda, dtype)
+        ref.particle_means = torch.tensor(g[pre + 'means_pre'], device=cuda)
+        want = ref.optimize(_eps=eps, **obs)[4]
+        assert rel(out[4].cpu().numpy(), want.cpu().numpy()) < 2e-5
+    else:
+        assert rel(out[4].cpu().numpy(), g[pre + 'costs']) < max(ftol, 1e-10)
+        assert rel(out[5].cpu().numpy(), g[pre + 'grad']) < max(10 * ftol, 1e-9)
+        assert rel(pl.particle_means.cpu().numpy(), g[pre + 'means_post']) < ftol
+
+
 def test_user_defined_term_on_a_problem_batch(cuda):
     """A user term on StochGPMPBatch sees trajs [B*NP*S, T, d] in (problem, particle, sample) order: a batch of B problems with a
     user-written velocity penalty == B single planners with the same term (problem_offset = b), over two iterations."""
