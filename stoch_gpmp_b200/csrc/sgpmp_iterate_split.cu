@@ -28,7 +28,7 @@
 #include "sgpmp_rng.cuh"
 
 #ifndef SGPMP_SPLIT_TS
-#define SGPMP_SPLIT_TS 4        // time steps per ring stage
+#define SGPMP_SPLIT_TS 5        // time steps per ring stage (C4: 1 / 2 / 3 / 4 / 5 steps 13.77 / 13.62 / 13.32 / 13.21 / 13.11 ms; 6 no longer fits four CTAs per SM)
 #endif
 #ifndef SGPMP_SPLIT_NSTG
 #define SGPMP_SPLIT_NSTG 2      // ring stages per warp pair
