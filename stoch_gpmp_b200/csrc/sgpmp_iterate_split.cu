@@ -410,6 +410,34 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                 // The sweep is instantiated for the common sphere counts as compile-time constants (oc = 0: run-time loop).
                 auto link_sweep = [&](auto oc) {
                     constexpr int OC = decltype(oc)::value;
+                    if constexpr (R == 1) {
+                        // one state warp per link warp (every shipped configuration): the field sums of the whole sweep stay in
+                        // registers and reach shared memory once, at the end (the per-stage fold of the general form below costs
+                        // ~16 instructions per stage on the warps that are the critical path)
+                        const int w = wb;
+                        TrajCostPairs<N, CHAIN> tc;
+                        tc.begin();
+                        for (int t0 = 1; t0 < T; t0 += TS) {
+                            const uint32_t stg = sc % NSTG, use = sc / NSTG;
+                            const int tend = min(t0 + TS, T);
+                            mbar_wait(bar_full(w, stg), use & 1u);
+                            const float2* slot = ring + ((size_t)(w * NSTG + stg) * TS) * SLOT + lane;
+#pragma unroll 1
+                            for (int t = t0; t < tend; ++t, slot += SLOT) {
+                                F2 xq[NP2];
+                                xq[0] = ld_f2(slot); xq[1] = ld_f2(slot + 32); xq[2] = ld_f2(slot + 64);
+                                xq[3] = f2(0.f, 0.f);
+                                tc.template link_fields<OC>(P, sm, xq);
+                            }
+                            mbar_arrive(bar_empty(w, stg));
+                            ++sc;
+                        }
+                        float4* ba = reinterpret_cast<float4*>(bacc + (size_t)(w * 32 + lane) * 8);
+                        ba[0] = make_float4(lane0(tc.a01), lane1(tc.a01), lane0(tc.a23), lane1(tc.a23));
+                        ba[1] = make_float4(lane0(tc.a45), lane1(tc.a45), tc.c_self, 0.f);
+                        mbar_arrive(bar_res(w));                         // the sums of the sweep are complete
+                        return;
+                    }
                     for (int t0 = 1; t0 < T; t0 += TS) {
                         const uint32_t stg = sc % NSTG, use = sc / NSTG;
                         const int tend = min(t0 + TS, T);
