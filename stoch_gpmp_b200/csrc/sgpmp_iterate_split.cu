@@ -39,6 +39,9 @@
 #ifndef SGPMP_SPLIT_UNROLL_A
 #define SGPMP_SPLIT_UNROLL_A 1  // unroll factor of the state warps' step loop
 #endif
+#ifndef SGPMP_SPLIT_UNROLL_B
+#define SGPMP_SPLIT_UNROLL_B 1  // unroll factor of the link warps' step loop
+#endif
 #ifndef SGPMP_SPLIT_SLEEP_NS
 #define SGPMP_SPLIT_SLEEP_NS 64 // back-off of a warp that finds its mbarrier phase incomplete (form without the suspend-time hint)
 #endif
@@ -128,7 +131,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
     static_assert(CHAIN == 0 || N == 7, "Panda structure has 7 joints");
     static_assert(NP2 <= 4, "start / goal staging holds up to 8 DoF");
     constexpr int TS = NB ? SGPMP_SPLIT_TS : 16;      // state-only form: a 'stage' is just the span of the two-level GP sum
-    constexpr int NSTG = SGPMP_SPLIT_NSTG, UNROLL_A = SGPMP_SPLIT_UNROLL_A;
+    constexpr int NSTG = SGPMP_SPLIT_NSTG, UNROLL_A = SGPMP_SPLIT_UNROLL_A, UNROLL_B = SGPMP_SPLIT_UNROLL_B;
     constexpr int SLOT = 3 * 32;                                      // float2 per (state warp, step): q pairs 0..2 x 32 lanes
     const int T = A.T, S = A.S, G = A.G, K = A.K;
     const int M = T * d, Mpad = (M + 3) & ~3, Spad = (S + 3) & ~3, NCH = (S + 31) >> 5;
@@ -422,7 +425,7 @@ iterate_split_kernel(const __grid_constant__ CostParams<float> P, const __grid_c
                             const int tend = min(t0 + TS, T);
                             mbar_wait(bar_full(w, stg), use & 1u);
                             const float2* slot = ring + ((size_t)(w * NSTG + stg) * TS) * SLOT + lane;
-#pragma unroll 1
+#pragma unroll UNROLL_B
                             for (int t = t0; t < tend; ++t, slot += SLOT) {
                                 F2 xq[NP2];
                                 xq[0] = ld_f2(slot); xq[1] = ld_f2(slot + 32); xq[2] = ld_f2(slot + 64);
